@@ -1,0 +1,139 @@
+"""CPU tests that pin the oracle: against the committed golden vectors (tests/golden, produced by the real
+reference `knn` and by the pure-PyTorch Chamfer formulation), against float64, and against torch.autograd."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu_oracle as O
+from oracle import torch_formulation as TF
+from tests.helpers import GOLDEN, assert_close_rel, assert_knn_equivalent, make_cloud_cn, make_pair
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "knn_*.npz"))), ids=os.path.basename)
+def test_knn_oracle_matches_reference_golden(path):
+    z = np.load(path)
+    x, k, ref = z["x"], int(z["k"]), z["idx"]
+    idx, pd = O.knn_f32(x, k, return_pd=True)
+    assert_knn_equivalent(idx, ref, pd, os.path.basename(path))
+    if "far" not in path:  # no exact ties in these fixtures: the restatement is index-for-index identical
+        assert (idx == ref).all()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "chamfer_*.npz"))), ids=os.path.basename)
+def test_chamfer_oracle_matches_formulation_golden(path):
+    z = np.load(path)
+    p1, p2 = z["p1"], z["p2"]
+    d1, d2, i1, i2, loss = O.chamfer_fwd(p1, p2)
+    assert (i1 == z["idx1"]).all() and (i2 == z["idx2"]).all()
+    assert_close_rel(d1, z["dist1"], 1e-5, "dist1")
+    assert_close_rel(d2, z["dist2"], 1e-5, "dist2")
+    assert_close_rel(loss, z["loss"], 1e-5, "loss")
+    B, N = d1.shape
+    M = d2.shape[1]
+    g1 = np.full((B, N), 1.0 / N, np.float32)
+    g2 = np.full((B, M), 1.0 / M, np.float32)
+    gp1, gp2 = O.chamfer_bwd(p1, p2, i1, i2, g1, g2)
+    assert_close_rel(gp1, z["grad_p1"], 1e-5, "grad_p1")
+    assert_close_rel(gp2, z["grad_p2"], 1e-5, "grad_p2")
+
+
+@pytest.mark.parametrize("B,N,M,kind", [(3, 200, 177, "decoder"), (2, 129, 300, "uniform"), (1, 1, 1, "decoder"),
+                                        (2, 1, 50, "decoder"), (2, 50, 1, "uniform")])
+def test_sided_distance_f32_vs_f64(B, N, M, kind):
+    p1, p2 = make_pair(B, N, M, seed=7, kind=kind)
+    d32, i32 = O.sided_distance_f32(p1.numpy(), p2.numpy())
+    d64, i64, gap = O.sided_distance_f64(p1.numpy(), p2.numpy())
+    assert_close_rel(d32, d64, 1e-5, "dist")
+    # wherever float64 sees a clear winner (gap above FP32 resolution of the distances) the FP32 index agrees
+    clear = gap > 1e-5 * np.maximum(d64, 1e-12)
+    assert (i32[clear] == i64[clear]).all()
+
+
+def test_ties_resolve_to_lowest_index():
+    p2 = np.zeros((1, 6, 3), np.float32)
+    p2[0, :, 0] = [1, 1, 2, 2, 1, 3]
+    p1 = np.array([[[1, 0, 0], [2, 0, 0], [2.5, 0, 0]]], np.float32)
+    d, i = O.sided_distance_f32(p1, p2)
+    assert i.tolist() == [[0, 2, 2]]
+    assert d.tolist() == [[0.0, 0.0, 0.25]]
+    d2, i2 = O.sided_distance_f32(p2, p1)
+    assert i2.tolist() == [[0, 0, 1, 1, 0, 2]]
+
+
+def test_identical_clouds_zero_loss_zero_grad():
+    p1, _ = make_pair(2, 77, 77, seed=3)
+    d1, d2, i1, i2, loss = O.chamfer_fwd(p1.numpy(), p1.numpy())
+    assert (d1 == 0).all() and (d2 == 0).all() and (loss == 0).all()
+    assert (i1 == np.arange(77)).all() and (i2 == np.arange(77)).all()
+    g = np.ones((2, 77), np.float32)
+    gp1, gp2 = O.chamfer_bwd(p1.numpy(), p1.numpy(), i1, i2, g, g)
+    assert (gp1 == 0).all() and (gp2 == 0).all()
+
+
+@pytest.mark.parametrize("need_p2", [True, False])
+def test_backward_vs_autograd_random_upstream(need_p2):
+    p1, p2 = make_pair(3, 90, 120, seed=11)
+    g = torch.Generator().manual_seed(5)
+    g1 = torch.randn(3, 90, generator=g)
+    g2 = torch.randn(3, 120, generator=g)
+    a = p1.clone().requires_grad_(True)
+    b = p2.clone().requires_grad_(True)
+    d1, i1 = TF.sided_distance_torch(a, b)
+    d2, i2 = TF.sided_distance_torch(b, a)
+    ((d1 * g1).sum() + (d2 * g2).sum()).backward()
+    gp1, gp2 = O.chamfer_bwd(p1.numpy(), p2.numpy(), i1.numpy(), i2.numpy(), g1.numpy(), g2.numpy(), True, need_p2)
+    assert_close_rel(gp1, a.grad.numpy(), 1e-5, "grad_p1")
+    if need_p2:
+        assert_close_rel(gp2, b.grad.numpy(), 1e-5, "grad_p2")
+    else:
+        assert gp2 is None
+
+
+def test_clustered_cloud_max_scatter_contention():
+    # every p1 point identical: all of p2 maps to index 0, so grad_p1[0] collects M scattered terms
+    p1 = np.full((1, 40, 3), 0.25, np.float32)
+    _, p2 = make_pair(1, 40, 64, seed=2)
+    d1, d2, i1, i2, _ = O.chamfer_fwd(p1, p2.numpy())
+    assert (i2 == 0).all()
+    a = torch.tensor(p1, requires_grad=True)
+    TF.chamfer_distance_torch(a, p2).sum().backward()
+    gp1, _ = O.chamfer_bwd(p1, p2.numpy(), i1, i2, np.full((1, 40), 1 / 40, np.float32),
+                           np.full((1, 64), 1 / 64, np.float32), True, False)
+    assert_close_rel(gp1, a.grad.numpy(), 1e-5, "grad_p1")
+
+
+@pytest.mark.parametrize("C,N,k", [(3, 100, 20), (64, 80, 20), (128, 70, 5), (3, 33, 33), (3, 40, 1), (5, 64, 7)])
+def test_knn_oracle_vs_torch_restatement_and_f64(C, N, k):
+    x = make_cloud_cn(2, C, N, seed=C + N)
+    idx, pd = O.knn_f32(x.numpy(), k, return_pd=True)
+    ref = TF.knn_torch(x, k).numpy()
+    # same FP32 values at the chosen neighbours (torch's matmul/sum may round differently for large C, hence
+    # the comparison runs on torch's own matrix as well)
+    inner = -2 * torch.matmul(x.transpose(2, 1), x)
+    xx = torch.sum(x ** 2, dim=1, keepdim=True)
+    pdt = (-xx - inner - xx.transpose(2, 1)).numpy()
+    va = np.take_along_axis(pdt, idx, 2)
+    vb = np.take_along_axis(pdt, ref, 2)
+    scale = float((x ** 2).sum(1).max())
+    assert np.abs(va - vb).max() <= 8 * np.finfo(np.float32).eps * scale
+    # float64 cross-check: the k-th chosen distance is within FP32 noise of the true k-th smallest distance
+    pd64 = O.knn_pd_f64(x.numpy())
+    kth_true = -np.sort(-pd64, axis=2)[:, :, k - 1]
+    kth_mine = np.take_along_axis(pd64, idx, 2).min(axis=2)
+    assert np.abs(kth_true - kth_mine).max() <= 16 * np.finfo(np.float32).eps * scale
+    # self is always the nearest neighbour for well-separated points
+    if C == 3:
+        assert (idx[:, :, 0] == np.arange(N)[None, :]).all()
+
+
+def test_oracle_thread_count_does_not_change_results():
+    p1, p2 = make_pair(4, 64, 64, seed=9)
+    O.set_threads(1)
+    a = O.chamfer_fwd(p1.numpy(), p2.numpy())
+    O.set_threads(0)
+    b = O.chamfer_fwd(p1.numpy(), p2.numpy())
+    for u, v in zip(a, b):
+        assert (u == v).all()
