@@ -1,0 +1,70 @@
+"""ctypes loader for libfpsg_b200.so (C ABI in include/fpsg_b200.h).
+
+There is deliberately no fallback of any kind: if the shared object is missing or a call fails, the caller gets
+a RuntimeError. Build it with ``python fpsg_b200/build.py`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .build import LIB
+
+ABI_VERSION = 1
+KNN_MAX_K = 128
+
+_f32p = ctypes.c_void_p  # device pointers travel as integers
+_i64p = ctypes.c_void_p
+_lib = None
+
+
+class FpsgError(RuntimeError):
+    pass
+
+
+def _declare(L: ctypes.CDLL) -> None:
+    c_int, c_size_t, c_float, vp = ctypes.c_int, ctypes.c_size_t, ctypes.c_float, ctypes.c_void_p
+    L.fpsg_abi_version.restype = c_int
+    L.fpsg_abi_version.argtypes = []
+    L.fpsg_last_error.restype = ctypes.c_char_p
+    L.fpsg_last_error.argtypes = []
+    L.fpsg_chamfer_fwd_workspace_bytes.restype = c_size_t
+    L.fpsg_chamfer_fwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    L.fpsg_chamfer_fwd.restype = c_int
+    L.fpsg_chamfer_fwd.argtypes = [vp, vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, c_size_t, vp]
+    L.fpsg_chamfer_bwd_workspace_bytes.restype = c_size_t
+    L.fpsg_chamfer_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    L.fpsg_chamfer_bwd.restype = c_int
+    L.fpsg_chamfer_bwd.argtypes = [vp, vp, vp, vp, vp, vp, c_int, c_int, c_int, vp, vp, vp, c_size_t, vp]
+    L.fpsg_chamfer_loss_fwd.restype = c_int
+    L.fpsg_chamfer_loss_fwd.argtypes = [vp, vp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, vp, c_size_t, vp]
+    L.fpsg_chamfer_loss_bwd.restype = c_int
+    L.fpsg_chamfer_loss_bwd.argtypes = [vp, vp, vp, vp, vp, c_float, c_float, c_int, c_int, c_int, vp, vp, vp, c_size_t, vp]
+    L.fpsg_knn_workspace_bytes.restype = c_size_t
+    L.fpsg_knn_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    L.fpsg_knn_fwd.restype = c_int
+    L.fpsg_knn_fwd.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]
+    L.fpsg_probe_fp32_peak.restype = c_int
+    L.fpsg_probe_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library. Raises if it has not been built: the product never runs without its CUDA code."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise FpsgError(f"{LIB} is missing: build it with `python fpsg_b200/build.py` "
+                            "(fpsg_b200 has no CPU or PyTorch fallback)")
+        L = ctypes.CDLL(LIB)
+        _declare(L)
+        got = L.fpsg_abi_version()
+        if got != ABI_VERSION:
+            raise FpsgError(f"libfpsg_b200.so ABI version {got}, host code expects {ABI_VERSION}: rebuild")
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().fpsg_last_error().decode("utf-8", "replace")
+        raise FpsgError(f"fpsg_b200 error {rc}: {msg}")

@@ -1,0 +1,38 @@
+"""``knn(x, k)`` of the DGCNN encoder on B200 (reference src/dgcnn/model.py:13-20), same signature and result
+contract: x (B,C,N) float32 CUDA -> LongTensor (B,N,k), nearest first, self included. Non-differentiable, like the
+reference's ``topk(...)[1]``."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def knn(x: torch.Tensor, k: int) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"x must be a torch.Tensor, got {type(x).__name__}")
+    if not x.is_cuda:
+        raise RuntimeError("x must be a CUDA tensor (fpsg_b200 has no CPU fallback)")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"x must be float32, got {x.dtype}")
+    if x.dim() != 3:
+        raise RuntimeError(f"x must have shape (B, C, N), got {tuple(x.shape)}")
+    B, C, N = x.shape
+    k = int(k)
+    if not (1 <= k <= N):
+        # torch.topk raises RuntimeError("selected index k out of range") here
+        raise RuntimeError(f"selected index k out of range: k={k}, N={N}")
+    if k > _lib.KNN_MAX_K:
+        raise RuntimeError(f"k={k} exceeds the supported maximum {_lib.KNN_MAX_K}")
+    x = x.detach().contiguous()
+    idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+    if B == 0:
+        return idx
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        nbytes = L.fpsg_knn_workspace_bytes(B, C, N, k)
+        ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=x.device)
+        rc = L.fpsg_knn_fwd(x.data_ptr(), B, C, N, k, idx.data_ptr(), ws.data_ptr(), nbytes,
+                            torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(rc)
+    return idx

@@ -1,0 +1,48 @@
+"""Drop-in shims that let the reference's source run unchanged on top of fpsg_b200.
+
+``install()`` does two things:
+  * registers ``kaolin``, ``kaolin.metrics`` and ``kaolin.metrics.pointcloud`` in ``sys.modules`` (unless a real
+    Kaolin is importable and ``force`` is False), so that ``from kaolin.metrics.pointcloud import
+    chamfer_distance`` (reference src/models/few_shot.py:13) resolves to the B200 implementation;
+  * if the reference's ``dgcnn.model`` module is (or later becomes) importable, rebinds its module-level ``knn``
+    to ``fpsg_b200.knn`` -- ``get_graph_feature`` looks ``knn`` up at call time (src/dgcnn/model.py:28).
+
+Alternatively put ``fpsg_b200/shims`` on ``PYTHONPATH``: the ``kaolin`` package in this directory is a regular
+importable package.
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.util
+import sys
+
+
+def install(force: bool = False, patch_dgcnn: bool = True) -> None:
+    have_real = False
+    if not force and "kaolin" not in sys.modules:
+        try:
+            have_real = importlib.util.find_spec("kaolin") is not None
+        except (ImportError, ValueError):
+            have_real = False
+    if force or not have_real:
+        from .kaolin import metrics as _metrics  # noqa: F401
+        from . import kaolin as _kaolin
+        from .kaolin.metrics import pointcloud as _pc
+        sys.modules["kaolin"] = _kaolin
+        sys.modules["kaolin.metrics"] = _metrics
+        sys.modules["kaolin.metrics.pointcloud"] = _pc
+    if patch_dgcnn:
+        patch_dgcnn_knn()
+
+
+def patch_dgcnn_knn(module=None) -> bool:
+    """Rebinds ``knn`` in the reference's dgcnn.model (already imported, or given). Returns True if patched."""
+    from ..knn import knn
+    mods = [module] if module is not None else [m for n, m in list(sys.modules.items())
+                                                if n in ("dgcnn.model", "src.dgcnn.model") and m is not None]
+    done = False
+    for m in mods:
+        if hasattr(m, "knn") and hasattr(m, "get_graph_feature"):
+            m.knn = knn
+            done = True
+    return done

@@ -1,0 +1,88 @@
+/*
+ * fpsg_b200.h -- C ABI of libfpsg_b200.so: the B200 (sm_100a) implementation of FPSG's point-set-distance
+ * hot path. Plain pointers and sizes only; no torch types. All pointers are DEVICE pointers unless a name
+ * ends in _host. Every function is re-entrant, enqueues work on `stream` and returns without synchronising
+ * (CUDA-graph capturable); the caller owns every buffer, including the workspace, and makes the buffers'
+ * device current before calling (torch's device guard does). Outputs are fully overwritten; nothing needs
+ * pre-zeroing. Return value: 0 on success, negative FPSG_E* on failure with a message in fpsg_last_error().
+ *
+ * What each entry point replaces in the reference (voidstrike/FPSG, paths relative to /root/reference):
+ *
+ *   fpsg_chamfer_fwd / fpsg_chamfer_bwd
+ *       the forward / backward of `kaolin.metrics.pointcloud.sided_distance` x2 inside
+ *       `chamfer_distance`, imported at src/models/few_shot.py:13, bound at :57, called at :110, :117, :167
+ *       (Kaolin 0.9.0's `_C.metrics.sided_distance_forward_cuda` / `_backward_cuda`).
+ *   fpsg_chamfer_loss_fwd / fpsg_chamfer_loss_bwd
+ *       the same plus the reduction glue `w1*mean + w2*mean` and the uniform upstream gradient produced by
+ *       `.sum()` at src/models/few_shot.py:110,117.
+ *   fpsg_knn_fwd
+ *       `knn(x, k)` at src/dgcnn/model.py:13-20 (called from get_graph_feature, :28).
+ *
+ * INTEGRATION.md shows the reference-side bindings (ctypes) a maintainer would add.
+ */
+#ifndef FPSG_B200_H_
+#define FPSG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPSG_ABI_VERSION 1
+
+#define FPSG_OK 0
+#define FPSG_EINVAL (-1)     /* bad shape / null pointer / unsupported size */
+#define FPSG_EWORKSPACE (-2) /* workspace missing or too small              */
+#define FPSG_ECUDA (-3)      /* a CUDA runtime call failed                  */
+
+typedef void* fpsg_stream_t; /* a cudaStream_t */
+
+int fpsg_abi_version(void);
+/* Thread-local, valid until the next failing call on the same thread. Never NULL. */
+const char* fpsg_last_error(void);
+
+/* ---- Chamfer / sided distance, squared L2, FP32 ------------------------------------------------------- */
+/* p1 (B,N,3), p2 (B,M,3) row-major FP32. dist1 (B,N), idx1 (B,N) int64: nearest p2 point of each p1 point;
+ * dist2 (B,M), idx2 (B,M): nearest p1 point of each p2 point. Lowest index wins exact ties. N, M >= 1. */
+size_t fpsg_chamfer_fwd_workspace_bytes(int B, int N, int M);
+int fpsg_chamfer_fwd(const float* p1, const float* p2, int B, int N, int M, float* dist1, float* dist2,
+                     int64_t* idx1, int64_t* idx2, void* ws, size_t ws_bytes, fpsg_stream_t stream);
+
+/* g1 (B,N), g2 (B,M): upstream gradients of dist1 / dist2. gp1 (B,N,3) and gp2 (B,M,3) are each optional
+ * (NULL = not requested, as for the ground-truth cloud in the reference's training loss). */
+size_t fpsg_chamfer_bwd_workspace_bytes(int B, int N, int M);
+int fpsg_chamfer_bwd(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2, const float* g1,
+                     const float* g2, int B, int N, int M, float* gp1, float* gp2, void* ws, size_t ws_bytes,
+                     fpsg_stream_t stream);
+
+/* Fused loss: loss[b] = w1 * mean_i dist1[b,i] + w2 * mean_j dist2[b,j]  (what kaolin's chamfer_distance
+ * returns). dist1/dist2 are optional outputs here (NULL = not wanted); idx1/idx2 are required (the backward
+ * consumes them). Uses the same workspace size as fpsg_chamfer_fwd. */
+int fpsg_chamfer_loss_fwd(const float* p1, const float* p2, int B, int N, int M, float w1, float w2, float* loss,
+                          float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, void* ws, size_t ws_bytes,
+                          fpsg_stream_t stream);
+/* gloss (B,): upstream gradient of loss; equivalent to fpsg_chamfer_bwd with g1 = gloss*w1/N, g2 = gloss*w2/M. */
+int fpsg_chamfer_loss_bwd(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2,
+                          const float* gloss, float w1, float w2, int B, int N, int M, float* gp1, float* gp2,
+                          void* ws, size_t ws_bytes, fpsg_stream_t stream);
+
+/* ---- kNN graph ------------------------------------------------------------------------------------------ */
+/* x (B,C,N) channel-major FP32; idx (B,N,k) int64: the k nearest points of every point (self included),
+ * nearest first, ranked by the reference's FP32 expression -|xi|^2 + 2 xi.xj - |xj|^2; equal values are
+ * ordered by ascending index. 1 <= k <= min(N, FPSG_KNN_MAX_K). */
+#define FPSG_KNN_MAX_K 128
+size_t fpsg_knn_workspace_bytes(int B, int C, int N, int k);
+int fpsg_knn_fwd(const float* x, int B, int C, int N, int k, int64_t* idx, void* ws, size_t ws_bytes,
+                 fpsg_stream_t stream);
+
+/* ---- Roofline probe -------------------------------------------------------------------------------------- */
+/* Runs a dependent-free FFMA chain on every SM and returns the achieved FP32 rate in TFLOP/s (2 FLOP per
+ * FFMA per lane) through *tflops_host; synchronises `stream`. Used by bench.py as the measured FP32 peak. */
+int fpsg_probe_fp32_peak(double* tflops_host, double* sm_mhz_host, fpsg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPSG_B200_H_ */

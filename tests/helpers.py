@@ -36,15 +36,17 @@ def make_cloud_cn(B: int, C: int, N: int, seed: int = 1234):
     return torch.randn(B, C, N, generator=g)
 
 
-def assert_close_rel(actual, expected, rel=1e-5, what=""):
-    """|a-e| <= rel * max(|e|, scale) elementwise, scale = max|expected| * 1e-3 guards exact zeros / cancellation
-    in sums of signed terms (gradients). rel=1e-5 is the north-star tolerance for distances and gradients."""
+def assert_close_rel(actual, expected, rel=1e-5, what="", scale_frac=1e-3):
+    """|a-e| <= rel * max(|e|, scale) elementwise, scale = max|expected| * scale_frac guards exact zeros /
+    cancellation in sums of signed terms (gradients). rel=1e-5 is the north-star tolerance for distances and
+    gradients. scale_frac=1.0 makes the test norm-wise (used only where the two sides round the upstream
+    gradient differently, so cancellation legitimately amplifies the per-element relative error)."""
     a = np.asarray(actual, dtype=np.float64)
     e = np.asarray(expected, dtype=np.float64)
     assert a.shape == e.shape, f"{what}: shape {a.shape} vs {e.shape}"
     if a.size == 0:
         return
-    scale = max(float(np.abs(e).max()) * 1e-3, 1e-30)
+    scale = max(float(np.abs(e).max()) * scale_frac, 1e-30)
     err = np.abs(a - e) / np.maximum(np.abs(e), scale)
     worst = float(err.max())
     assert worst <= rel, f"{what}: max relative error {worst:.3e} > {rel:.1e} at {np.unravel_index(err.argmax(), err.shape)}"

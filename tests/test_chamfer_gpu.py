@@ -1,0 +1,252 @@
+"""GPU parity tests for the Chamfer path: the CUDA library (through the C ABI via fpsg_b200's host code) against
+the CPU oracle on identical seeded inputs. Gate (BASELINE.json north_star): indices bit-exact (the oracle's
+lowest-index tie rule is reproduced, so even exact ties must agree), distances and gradients within 1e-5
+relative -- in practice the distances are bit-identical because the FP32 instruction sequence is the oracle's."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import GOLDEN, assert_close_rel, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import cpu_oracle
+    return cpu_oracle
+
+
+def _run_fwd(p1, p2):
+    import fpsg_b200
+    d1, d2, i1, i2 = fpsg_b200.chamfer_distance(p1.cuda(), p2.cuda())
+    torch.cuda.synchronize()
+    return d1.cpu().numpy(), d2.cpu().numpy(), i1.cpu().numpy(), i2.cpu().numpy()
+
+
+SHAPES = [
+    (1, 1, 1), (2, 1, 70), (2, 70, 1), (3, 31, 33), (2, 64, 64), (1, 513, 129), (2, 2047, 2049), (1, 2049, 2047),
+    (37, 100, 90), (4, 2048, 2048), (1, 4100, 300), (2, 300, 4100), (1, 5000, 5000),
+]
+
+
+@pytest.mark.parametrize("B,N,M", SHAPES)
+@pytest.mark.parametrize("kind", ["decoder", "uniform"])
+def test_forward_bit_exact_vs_oracle(B, N, M, kind):
+    O = _oracle()
+    p1, p2 = make_pair(B, N, M, seed=1234 + N + M, kind=kind)
+    d1, d2, i1, i2 = _run_fwd(p1, p2)
+    od1, od2, oi1, oi2, _ = O.chamfer_fwd(p1.numpy(), p2.numpy())
+    assert i1.dtype == np.int64 and i2.dtype == np.int64
+    assert (i1 == oi1).all(), f"idx1 mismatches: {(i1 != oi1).sum()}"
+    assert (i2 == oi2).all(), f"idx2 mismatches: {(i2 != oi2).sum()}"
+    assert_close_rel(d1, od1, 1e-5, "dist1")
+    assert_close_rel(d2, od2, 1e-5, "dist2")
+    assert (d1 == od1).all() and (d2 == od2).all(), "distances expected bit-identical to the oracle"
+
+
+def test_exact_ties_resolve_to_lowest_index():
+    O = _oracle()
+    g = torch.Generator().manual_seed(3)
+    # integer grid coordinates: lots of exactly equal distances
+    p1 = torch.randint(-3, 4, (3, 300, 3), generator=g).float()
+    p2 = torch.randint(-3, 4, (3, 257, 3), generator=g).float()
+    d1, d2, i1, i2 = _run_fwd(p1, p2)
+    od1, od2, oi1, oi2, _ = O.chamfer_fwd(p1.numpy(), p2.numpy())
+    assert (i1 == oi1).all() and (i2 == oi2).all()
+    assert (d1 == od1).all() and (d2 == od2).all()
+    # duplicated points inside one cloud
+    q = torch.randn(1, 50, 3, generator=g)
+    p2 = torch.cat([q, q, q], dim=1)
+    d1, d2, i1, i2 = _run_fwd(q, p2)
+    assert (i1 == np.arange(50)[None]).all() and (d1 == 0).all()
+    assert (i2 == np.concatenate([np.arange(50)] * 3)[None]).all()
+
+
+def test_identical_clouds_zero_distance_zero_grad():
+    import fpsg_b200
+    p, _ = make_pair(2, 777, 777, seed=5)
+    a = p.cuda().requires_grad_(True)
+    b = p.cuda().clone().requires_grad_(True)
+    d1, d2, i1, i2 = fpsg_b200.chamfer_distance(a, b)
+    assert (d1 == 0).all() and (d2 == 0).all()
+    assert (i1.cpu() == torch.arange(777)).all() and (i2.cpu() == torch.arange(777)).all()
+    (d1.sum() + d2.sum()).backward()
+    assert (a.grad == 0).all() and (b.grad == 0).all()
+
+
+def test_large_magnitude_coordinates():
+    O = _oracle()
+    p1, p2 = make_pair(2, 500, 400, seed=8)
+    p1 = p1 * 100 + 50
+    p2 = p2 * 100 + 50
+    d1, d2, i1, i2 = _run_fwd(p1, p2)
+    od1, od2, oi1, oi2, _ = O.chamfer_fwd(p1.numpy(), p2.numpy())
+    assert (i1 == oi1).all() and (i2 == oi2).all() and (d1 == od1).all() and (d2 == od2).all()
+
+
+@pytest.mark.parametrize("B,N,M", [(2, 64, 48), (3, 33, 130), (2, 1000, 777), (32, 2048, 2048)])
+def test_backward_vs_oracle_random_upstream(B, N, M):
+    import fpsg_b200
+    O = _oracle()
+    p1, p2 = make_pair(B, N, M, seed=77 + N)
+    g = torch.Generator().manual_seed(1)
+    g1 = torch.randn(B, N, generator=g)
+    g2 = torch.randn(B, M, generator=g)
+    a = p1.cuda().requires_grad_(True)
+    b = p2.cuda().requires_grad_(True)
+    d1, d2, i1, i2 = fpsg_b200.chamfer_distance(a, b)
+    assert not i1.requires_grad and not i2.requires_grad
+    ((d1 * g1.cuda()).sum() + (d2 * g2.cuda()).sum()).backward()
+    ogp1, ogp2 = O.chamfer_bwd(p1.numpy(), p2.numpy(), i1.cpu().numpy(), i2.cpu().numpy(), g1.numpy(), g2.numpy())
+    assert_close_rel(a.grad.cpu().numpy(), ogp1, 1e-5, "grad_p1")
+    assert_close_rel(b.grad.cpu().numpy(), ogp2, 1e-5, "grad_p2")
+
+
+def test_backward_only_p1_requires_grad_like_reference():
+    # ground truth never needs a gradient in the reference's loss (few_shot.py:109-117)
+    import fpsg_b200
+    O = _oracle()
+    p1, p2 = make_pair(5, 2048, 2048, seed=21)
+    a = p1.cuda().requires_grad_(True)
+    b = p2.cuda()
+    loss = fpsg_b200.chamfer_loss(a, b)
+    assert loss.shape == (5,)
+    loss.sum().backward()
+    od1, od2, oi1, oi2, oloss = O.chamfer_fwd(p1.numpy(), p2.numpy())
+    assert_close_rel(loss.detach().cpu().numpy(), oloss, 1e-6, "loss")
+    g1 = np.full((5, 2048), np.float32(1.0) / np.float32(2048), np.float32)
+    g2 = np.full((5, 2048), np.float32(1.0) / np.float32(2048), np.float32)
+    ogp1, _ = O.chamfer_bwd(p1.numpy(), p2.numpy(), oi1, oi2, g1, g2, True, False)
+    assert_close_rel(a.grad.cpu().numpy(), ogp1, 1e-5, "grad_p1")
+    assert b.grad is None
+
+
+def test_clustered_cloud_max_scatter_contention():
+    import fpsg_b200
+    O = _oracle()
+    p1 = torch.full((2, 3000, 3), 0.25)
+    _, p2 = make_pair(2, 10, 5000, seed=2)
+    a = p1.cuda().requires_grad_(True)
+    b = p2.cuda().requires_grad_(True)
+    d1, d2, i1, i2 = fpsg_b200.chamfer_distance(a, b)
+    assert (i2 == 0).all()
+    (d1.mean() + d2.mean()).backward()
+    g1 = np.full((2, 3000), 1 / 6000, np.float32)
+    g2 = np.full((2, 5000), 1 / 10000, np.float32)
+    ogp1, ogp2 = O.chamfer_bwd(p1.numpy(), p2.numpy(), i1.cpu().numpy(), i2.cpu().numpy(), g1, g2)
+    assert_close_rel(a.grad.cpu().numpy(), ogp1, 1e-5, "grad_p1")
+    assert_close_rel(b.grad.cpu().numpy(), ogp2, 1e-5, "grad_p2")
+
+
+@pytest.mark.parametrize("name", ["chamfer_small", "chamfer_ragged"])
+def test_golden_fixtures(name):
+    import fpsg_b200
+    z = np.load(f"{GOLDEN}/{name}.npz")
+    a = torch.tensor(z["p1"]).cuda().requires_grad_(True)
+    b = torch.tensor(z["p2"]).cuda().requires_grad_(True)
+    d1, d2, i1, i2 = fpsg_b200.chamfer_distance(a, b)
+    assert (i1.cpu().numpy() == z["idx1"]).all() and (i2.cpu().numpy() == z["idx2"]).all()
+    assert_close_rel(d1.detach().cpu().numpy(), z["dist1"], 1e-5, "dist1")
+    assert_close_rel(d2.detach().cpu().numpy(), z["dist2"], 1e-5, "dist2")
+    loss = fpsg_b200.chamfer_loss(a, b)
+    assert_close_rel(loss.detach().cpu().numpy(), z["loss"], 1e-5, "loss")
+    loss.sum().backward()
+    assert_close_rel(a.grad.cpu().numpy(), z["grad_p1"], 1e-5, "grad_p1")
+    assert_close_rel(b.grad.cpu().numpy(), z["grad_p2"], 1e-5, "grad_p2")
+
+
+def test_fused_loss_matches_composed_and_weights():
+    import fpsg_b200
+    p1, p2 = make_pair(7, 300, 200, seed=4)
+    a = p1.cuda().requires_grad_(True)
+    b = p2.cuda().requires_grad_(True)
+    d1, d2, _, _ = fpsg_b200.chamfer_distance(a, b)
+    ref = 0.5 * d1.mean(-1) + 2.0 * d2.mean(-1)
+    go = torch.randn(7, device="cuda")
+    (ref * go).sum().backward()
+    ga, gb = a.grad.clone(), b.grad.clone()
+    a.grad = None
+    b.grad = None
+    fused = fpsg_b200.chamfer_loss(a, b, 0.5, 2.0)
+    (fused * go).sum().backward()
+    assert_close_rel(fused.detach().cpu().numpy(), ref.detach().cpu().numpy(), 1e-6, "loss")
+    # torch's mean/mul backward rounds the per-element upstream gradient differently from (gloss*w)/N, so the
+    # two sums of signed terms are compared norm-wise
+    assert_close_rel(a.grad.cpu().numpy(), ga.cpu().numpy(), 1e-5, "grad_p1", scale_frac=1.0)
+    assert_close_rel(b.grad.cpu().numpy(), gb.cpu().numpy(), 1e-5, "grad_p2", scale_frac=1.0)
+
+
+def test_sided_distance_surface():
+    import fpsg_b200
+    O = _oracle()
+    p1, p2 = make_pair(3, 150, 220, seed=6)
+    a = p1.cuda().requires_grad_(True)
+    b = p2.cuda().requires_grad_(True)
+    d, i = fpsg_b200.sided_distance(a, b)
+    od, oi = O.sided_distance_f32(p1.numpy(), p2.numpy())
+    assert (i.cpu().numpy() == oi).all() and (d.detach().cpu().numpy() == od).all()
+    d.sum().backward()
+    ogp1, ogp2 = O.chamfer_bwd(p1.numpy(), p2.numpy(), oi, np.zeros((3, 220), np.int64), np.ones((3, 150), np.float32),
+                               np.zeros((3, 220), np.float32))
+    assert_close_rel(a.grad.cpu().numpy(), ogp1, 1e-5, "grad_p1")
+    assert_close_rel(b.grad.cpu().numpy(), ogp2, 1e-5, "grad_p2")
+
+
+def test_noncontiguous_and_offset_inputs():
+    O = _oracle()
+    p1, p2 = make_pair(4, 130, 140, seed=9)
+    big = torch.zeros(4, 131, 4)
+    big[:, 1:, :3] = p1
+    view = big.cuda()[:, 1:, :3]  # non-contiguous, misaligned start
+    assert not view.is_contiguous()
+    d1, d2, i1, i2 = _run_fwd(view, p2)
+    od1, od2, oi1, oi2, _ = O.chamfer_fwd(p1.numpy(), p2.numpy())
+    assert (i1 == oi1).all() and (i2 == oi2).all() and (d1 == od1).all()
+    # a contiguous tensor whose storage offset is only 4-byte aligned
+    flat = torch.zeros(4 * 130 * 3 + 1)
+    flat[1:] = p1.reshape(-1)
+    off = flat.cuda()[1:].view(4, 130, 3)
+    assert off.is_contiguous() and off.data_ptr() % 16 != 0
+    d1, d2, i1, i2 = _run_fwd(off, p2)
+    assert (i1 == oi1).all() and (i2 == oi2).all() and (d1 == od1).all() and (d2 == od2).all()
+
+
+def test_error_behaviour():
+    import fpsg_b200
+    ok = torch.zeros(2, 8, 3, device="cuda")
+    with pytest.raises(RuntimeError):
+        fpsg_b200.chamfer_distance(torch.zeros(2, 8, 3), torch.zeros(2, 8, 3))  # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        fpsg_b200.chamfer_distance(ok, torch.zeros(3, 8, 3, device="cuda"))    # batch mismatch
+    with pytest.raises(RuntimeError):
+        fpsg_b200.chamfer_distance(ok, torch.zeros(2, 8, 2, device="cuda"))    # last dim
+    with pytest.raises(RuntimeError):
+        fpsg_b200.chamfer_distance(ok.double(), ok.double())                   # dtype
+    with pytest.raises(RuntimeError):
+        fpsg_b200.chamfer_distance(ok, torch.zeros(2, 0, 3, device="cuda"))    # empty candidate cloud
+    d1, d2, i1, i2 = fpsg_b200.chamfer_distance(ok[:0], ok[:0])                  # empty batch is fine
+    assert d1.shape == (0, 8) and i2.shape == (0, 8)
+
+
+def test_full_size_properties_c1_and_c4():
+    """Size-independent properties at BASELINE.json sizes (the oracle is skipped at N=16384)."""
+    import fpsg_b200
+    for (B, N, M) in [(32, 2048, 2048), (2, 16384, 16384)]:
+        p1, p2 = make_pair(B, N, M, seed=1234)
+        a, b = p1.cuda(), p2.cuda()
+        d1, d2, i1, i2 = fpsg_b200.chamfer_distance(a, b)
+        # the reported distance is the distance to the reported neighbour
+        nn = torch.gather(b, 1, i1[..., None].expand(-1, -1, 3))
+        assert torch.allclose(((a - nn) ** 2).sum(-1), d1, rtol=1e-5, atol=0)
+        nn2 = torch.gather(a, 1, i2[..., None].expand(-1, -1, 3))
+        assert torch.allclose(((b - nn2) ** 2).sum(-1), d2, rtol=1e-5, atol=0)
+        # symmetry: swapping the arguments swaps the outputs exactly
+        e1, e2, j1, j2 = fpsg_b200.chamfer_distance(b, a)
+        assert torch.equal(e1, d2) and torch.equal(e2, d1) and torch.equal(j1, i2) and torch.equal(j2, i1)
+        # no candidate is closer than the reported one (checked on a sample of rows against a dense torch scan)
+        rows = torch.arange(0, N, max(1, N // 64), device="cuda")
+        dense = ((a[:, rows, None, :] - b[:, None, :, :]) ** 2).sum(-1)
+        assert (dense.min(-1)[0] >= d1[:, rows] * (1 - 1e-5)).all()
+        # idempotence / determinism
+        f1, f2, k1, k2 = fpsg_b200.chamfer_distance(a, b)
+        assert torch.equal(f1, d1) and torch.equal(k2, i2)

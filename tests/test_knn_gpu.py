@@ -1,0 +1,86 @@
+"""GPU parity tests for knn(x, k): CUDA library vs the CPU oracle (bit-exact, including tie order) and vs the
+golden outputs of the real reference function (exact up to permutations among exactly-equal FP32 values)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import GOLDEN, assert_knn_equivalent, make_cloud_cn
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import cpu_oracle
+    return cpu_oracle
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "knn_*.npz"))), ids=os.path.basename)
+def test_knn_matches_reference_golden(path):
+    import fpsg_b200
+    O = _oracle()
+    z = np.load(path)
+    x, k, ref = z["x"], int(z["k"]), z["idx"]
+    idx = fpsg_b200.knn(torch.tensor(x).cuda(), k).cpu().numpy()
+    _, pd = O.knn_f32(x, k, return_pd=True)
+    assert_knn_equivalent(idx, ref, pd, os.path.basename(path))
+    assert (idx == O.knn_f32(x, k)).all(), "bit-exact agreement with the oracle (tie order included)"
+
+
+@pytest.mark.parametrize("B,C,N,k", [(2, 3, 100, 20), (3, 3, 1024, 20), (2, 3, 1000, 1), (1, 3, 33, 33), (2, 3, 257, 64),
+                                     (1, 3, 300, 128), (2, 64, 300, 20), (2, 64, 1024, 20), (1, 128, 520, 20),
+                                     (2, 5, 77, 7), (1, 3, 9000, 20)])
+def test_knn_bit_exact_vs_oracle(B, C, N, k):
+    import fpsg_b200
+    O = _oracle()
+    x = make_cloud_cn(B, C, N, seed=B + C + N)
+    idx = fpsg_b200.knn(x.cuda(), k)
+    assert idx.dtype == torch.int64 and idx.shape == (B, N, k)
+    ref = O.knn_f32(x.numpy(), k)
+    got = idx.cpu().numpy()
+    assert (got == ref).all(), f"{(got != ref).sum()} of {ref.size} positions differ"
+
+
+def test_knn_duplicates_and_ties():
+    import fpsg_b200
+    O = _oracle()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randint(-2, 3, (2, 3, 200), generator=g).float()  # grid points: massive exact ties
+    got = fpsg_b200.knn(x.cuda(), 20).cpu().numpy()
+    assert (got == O.knn_f32(x.numpy(), 20)).all()
+
+
+def test_knn_vs_torch_reference_formula_on_gpu():
+    """Same-device check against the reference expression (src/dgcnn/model.py:13-20) evaluated by torch on the
+    GPU: neighbour values must agree to FP32 rounding of the expanded form."""
+    import fpsg_b200
+    from oracle.torch_formulation import knn_torch
+    for C in (3, 64, 128):
+        x = make_cloud_cn(4, C, 1024, seed=C).cuda()
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ref = knn_torch(x, 20)
+        got = fpsg_b200.knn(x, 20)
+        inner = -2 * torch.matmul(x.transpose(2, 1), x)
+        xx = torch.sum(x ** 2, dim=1, keepdim=True)
+        pd = -xx - inner - xx.transpose(2, 1)
+        va = torch.gather(pd, 2, got)
+        vb = torch.gather(pd, 2, ref)
+        scale = float(xx.max())
+        assert float((va - vb).abs().max()) <= 16 * np.finfo(np.float32).eps * scale
+        assert float((got == ref).float().mean()) > 0.995
+
+
+def test_knn_error_behaviour():
+    import fpsg_b200
+    x = torch.zeros(2, 3, 16, device="cuda")
+    with pytest.raises(RuntimeError):
+        fpsg_b200.knn(x.cpu(), 4)
+    with pytest.raises(RuntimeError):
+        fpsg_b200.knn(x, 17)
+    with pytest.raises(RuntimeError):
+        fpsg_b200.knn(x, 0)
+    with pytest.raises(RuntimeError):
+        fpsg_b200.knn(x.double(), 4)
+    assert fpsg_b200.knn(x[:0], 4).shape == (0, 16, 4)
