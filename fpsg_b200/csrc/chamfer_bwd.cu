@@ -43,7 +43,6 @@ __device__ __forceinline__ float uniform_weight(const float* g, float scale, flo
 __global__ void __launch_bounds__(kBwdThreads)
 chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
     __shared__ int sCount[kBwdThreads];
-    __shared__ int sStart[kBwdThreads];
     __shared__ int sCursor[kBwdThreads];
     __shared__ int sWarp[kBwdThreads / 32];
     __shared__ int sList[kBwdChunk];
@@ -65,13 +64,26 @@ chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
     const float uA = uniform ? __fmul_rn(2.0f, uniform_weight(S.gA, S.scaleA, S.divA, b)) : 0.f;
     const float uQ = uniform ? __fmul_rn(2.0f, uniform_weight(S.gQ, S.scaleQ, S.divQ, b)) : 0.f;
 
+    constexpr int kPer = kBwdChunk / kBwdThreads;  // arg-min indices of the other cloud per thread per chunk
+
+    // issue order matters more than arithmetic here (the kernel is a chain of L2 latencies): own point and its
+    // direct edge first, then the first chunk of the other cloud's indices, all in flight together
     float ax = 0.f, ay = 0.f, az = 0.f;
-    double gx = 0.0, gy = 0.0, gz = 0.0;
+    long long x = 0;
     if (live) {
+        x = S.idxA[(size_t)b * S.Na + i];
         ax = __ldg(Ab + 3 * i);
         ay = __ldg(Ab + 3 * i + 1);
         az = __ldg(Ab + 3 * i + 2);
-        const long long x = S.idxA[(size_t)b * S.Na + i];
+    }
+    long long t[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int jj = tid + q * kBwdThreads;
+        t[q] = jj < S.Nq ? iQ[jj] - i0 : -1;
+    }
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    if (live) {
         const float g = uniform ? uA : __fmul_rn(2.0f, __ldg(S.gA + (size_t)b * S.Na + i));
         gx = (double)__fmul_rn(g, __fsub_rn(ax, __ldg(Qb + 3 * x)));
         gy = (double)__fmul_rn(g, __fsub_rn(ay, __ldg(Qb + 3 * x + 1)));
@@ -80,13 +92,19 @@ chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
 
     for (int j0 = 0; j0 < S.Nq; j0 += kBwdChunk) {
         const int jn = min(kBwdChunk, S.Nq - j0);
+        if (j0 > 0) {
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+                const int jj = tid + q * kBwdThreads;
+                t[q] = jj < jn ? iQ[j0 + jj] - i0 : -1;
+            }
+        }
         sCount[tid] = 0;
         __syncthreads();
         // pass 1: bucket sizes
-        for (int jj = tid; jj < jn; jj += kBwdThreads) {
-            const long long t = iQ[j0 + jj] - i0;
-            if (t >= 0 && t < kBwdThreads) atomicAdd(&sCount[(int)t], 1);
-        }
+#pragma unroll
+        for (int q = 0; q < kPer; ++q)
+            if (t[q] >= 0 && t[q] < kBwdThreads) atomicAdd(&sCount[(int)t[q]], 1);
         __syncthreads();
         // exclusive scan of the 256 counts
         const int c = sCount[tid];
@@ -101,14 +119,12 @@ chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
         int base = 0;
         for (int q = 0; q < w; ++q) base += sWarp[q];
         const int start = base + incl - c;
-        sStart[tid] = start;
         sCursor[tid] = start;
         __syncthreads();
         // pass 2: fill
-        for (int jj = tid; jj < jn; jj += kBwdThreads) {
-            const long long t = iQ[j0 + jj] - i0;
-            if (t >= 0 && t < kBwdThreads) sList[atomicAdd(&sCursor[(int)t], 1)] = j0 + jj;
-        }
+#pragma unroll
+        for (int q = 0; q < kPer; ++q)
+            if (t[q] >= 0 && t[q] < kBwdThreads) sList[atomicAdd(&sCursor[(int)t[q]], 1)] = j0 + tid + q * kBwdThreads;
         __syncthreads();
         // gather: this thread's bucket
         if (live) {
