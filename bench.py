@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of fpsg_b200 (contract: see the task brief / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): Chamfer fwd+bwd pairs/s at B=32, N=M=2048 per GPU (weak scaling over 1/2/4/8 B200),
+plus the dominant kernel's fraction of the FP32 FMA roofline.
+
+A *step* = one pass of the hot path over one batch of 32 synthetic cloud pairs: fused Chamfer loss forward
+(sweep + finalize + loss kernels), backward to p1 (the ground truth has no gradient, as in the reference's
+training loss, src/models/few_shot.py:109-117), and -- for N > 1 -- the scalar loss all-reduce over NCCL.
+
+  value : whole-job pairs/s, inputs resident in HBM, the C ABI called directly, CUDA events, max over ranks.
+  e2e   : the same metric through the reference-facing Python call (the kaolin shim's
+          chamfer_distance(p1, p2).sum().backward()) with HOST (pinned) inputs: H2D copies and the D2H read of
+          the loss are inside the timed region.
+  roofline     : the sweep kernel timed alone (fpsg_chamfer_sweep_only) against the FP32 FMA peak measured in
+                 the same run by an FFMA micro-kernel (MEASURED_PEAKS.json has no FP32 row).
+  cpu_baseline : the reference's PyTorch CPU formulation (oracle/torch_formulation.py) on a bounded sample.
+
+`--impl reference` times that CPU formulation on the host cores as its own arm.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, N_PTS, M_PTS = 32, 2048, 2048
+WORKLOAD = "c1: Chamfer loss fwd+bwd(p1), B=32 per GPU, N=M=2048, synthetic xyz float32"
+METRIC = "chamfer_fwd_bwd_pairs_per_s"
+RING_SETS = 96  # distinct input batches cycled through: 96 x 1.57 MB = 151 MB > 126 MB L2
+# dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch, from profiles/r01_sweep_ncu_summary.md
+SWEEP_DRAM_TRAFFIC_BYTES = 1.59e6
+
+
+def make_inputs(batch, n, m, seed, device=None, pin=False):
+    """p1 = tanh(0.5*randn) (decoder-like), p2 = unit-ball normalised randn; seeded on CPU."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    p1 = torch.tanh(0.5 * torch.randn(batch, n, 3, generator=g))
+    p2 = torch.randn(batch, m, 3, generator=g)
+    p2 = p2 - p2.mean(1, keepdim=True)
+    p2 = p2 / p2.norm(dim=2).amax(1)[:, None, None]
+    if pin:
+        return p1.pin_memory(), p2.pin_memory()
+    if device is not None:
+        return p1.to(device), p2.to(device)
+    return p1, p2
+
+
+class ClockSampler:
+    """Polls nvidia-smi (the recipe's clocks line) while the timed region runs."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 9:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for p in self.rows:
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_formulation_pairs_per_s(sample_pairs: int, iters: int, threads: int | None = None):
+    """Times the reference's PyTorch CPU formulation (difference-form squared L2 -> min both ways -> mean+mean ->
+    sum -> backward to p1) on `sample_pairs` pairs of the c1 workload. Returns (pairs/s, threads, seconds/iter)."""
+    import torch
+    from oracle import torch_formulation as TF
+    if threads:
+        torch.set_num_threads(threads)
+    p1, p2 = make_inputs(sample_pairs, N_PTS, M_PTS, seed=1234 + 1)
+    best = None
+    for it in range(iters + 1):  # first iteration is the warm-up
+        a = p1.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        loss = TF.chamfer_distance_torch(a, p2, chunk=4)
+        loss.sum().backward()
+        dt = time.perf_counter() - t0
+        if it > 0:
+            best = dt if best is None else min(best, dt)
+    return sample_pairs / best, torch.get_num_threads(), best
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the CPU formulation on the box's host cores. Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    sample = 8
+    t_all0 = time.perf_counter()
+    rates = []
+    torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import torch_formulation as TF
+    p1, p2 = make_inputs(sample, N_PTS, M_PTS, seed=1234 + 1)
+
+    def step():
+        a = p1.clone().requires_grad_(True)
+        TF.chamfer_distance_torch(a, p2, chunk=4).sum().backward()
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    rates.append(value)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "each step is a bounded sample of 8 of the 32 pairs; value = pairs/s"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{sample} pairs x {args.steps} steps of the c1 workload, pure-PyTorch difference-form Chamfer fwd+bwd "
+                                   f"(oracle/torch_formulation.py; Kaolin 0.9.0 itself is absent), os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                         "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: fpsg_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from fpsg_b200 import _lib
+    import fpsg_b200
+    import fpsg_b200.shims
+    L = _lib.lib()
+    B, N, M = B_PER_GPU, N_PTS, M_PTS
+
+    # ---- FP32 peak probe (roofline denominator), same process, same GPU ----
+    tf, mhz = ctypes.c_double(), ctypes.c_double()
+    _lib.check(L.fpsg_probe_fp32_peak(ctypes.byref(tf), ctypes.byref(mhz), None))
+    fp32_peak_tflops, probe_mhz = tf.value, mhz.value
+
+    # ---- inputs: a ring of distinct batches larger than L2, resident in HBM ----
+    ring = [make_inputs(B, N, M, seed=1234 + 1 + 1000 * rank + s, device=dev) for s in range(RING_SETS)]
+    dist1 = torch.empty(B, N, device=dev)
+    dist2 = torch.empty(B, M, device=dev)
+    idx1 = torch.empty(B, N, dtype=torch.int64, device=dev)
+    idx2 = torch.empty(B, M, dtype=torch.int64, device=dev)
+    loss = torch.empty(B, device=dev)
+    gloss = torch.ones(B, device=dev)
+    gp1 = torch.empty(B, N, 3, device=dev)
+    total = torch.zeros((), device=dev)
+    nbytes = L.fpsg_chamfer_fwd_workspace_bytes(B, N, M)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+    ptrs = [(a.data_ptr(), b.data_ptr()) for a, b in ring]
+    o = (loss.data_ptr(), dist1.data_ptr(), dist2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), ws.data_ptr(), gloss.data_ptr(), gp1.data_ptr())
+
+    def step(i):
+        a, b = ptrs[i % RING_SETS]
+        _lib.check(L.fpsg_chamfer_loss_fwd(a, b, B, N, M, 1.0, 1.0, o[0], o[1], o[2], o[3], o[4], o[5], nbytes, sp))
+        if world > 1:
+            torch.sum(loss, out=total)
+            work = dist.all_reduce(total, op=dist.ReduceOp.SUM, async_op=True)
+        _lib.check(L.fpsg_chamfer_loss_bwd(a, b, o[3], o[4], o[6], 1.0, 1.0, B, N, M, o[7], None, None, 0, sp))
+        if world > 1:
+            work.wait()
+
+    kernels_per_step = 4  # sweep, finalize, loss, backward (the NCCL kernel for N > 1 is not ours)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+
+    # ---- dominant kernel alone (roofline), same ring, same stream ----
+    def sweep(i):
+        a, b = ptrs[i % RING_SETS]
+        _lib.check(L.fpsg_chamfer_sweep_only(a, b, B, N, M, o[5], nbytes, sp))
+    for i in range(5):
+        sweep(i)
+    torch.cuda.synchronize(dev)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_sweeps = max(50, min(args.steps, 400))
+    s0.record(stream)
+    for i in range(n_sweeps):
+        sweep(5 + i)
+    s1.record(stream)
+    torch.cuda.synchronize(dev)
+    sweep_us = s0.elapsed_time(s1) / n_sweeps * 1e3
+
+    # ---- backward kernel alone (HBM view) ----
+    def bwd(i):
+        a, b = ptrs[i % RING_SETS]
+        _lib.check(L.fpsg_chamfer_loss_bwd(a, b, o[3], o[4], o[6], 1.0, 1.0, B, N, M, o[7], None, None, 0, sp))
+    for i in range(5):
+        bwd(i)
+    torch.cuda.synchronize(dev)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record(stream)
+    for i in range(n_sweeps):
+        bwd(5 + i)
+    b1.record(stream)
+    torch.cuda.synchronize(dev)
+    bwd_us = b0.elapsed_time(b1) / n_sweeps * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: the reference-facing call, host (pinned) inputs, loss read back every step ----
+    fpsg_b200.shims.install(force=True)
+    from kaolin.metrics.pointcloud import chamfer_distance as shim_chamfer
+    host = [make_inputs(B, N, M, seed=777 + 1000 * rank + s, pin=True) for s in range(8)]
+    d1 = torch.empty(B, N, 3, device=dev)
+    d2 = torch.empty(B, M, 3, device=dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        h1, h2 = host[i % len(host)]
+        d1.copy_(h1, non_blocking=True)
+        d2.copy_(h2, non_blocking=True)
+        a = d1.requires_grad_(True)
+        val = shim_chamfer(a, d2).sum()
+        if world > 1:
+            red = val.detach().clone()
+            work = dist.all_reduce(red, op=dist.ReduceOp.SUM, async_op=True)
+        val.backward()
+        if world > 1:
+            work.wait()
+            loss_host.copy_(red, non_blocking=True)
+        else:
+            loss_host.copy_(val.detach(), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()  # the step's result is on the host
+        a.grad = None
+        d1.requires_grad_(False)
+        return float(loss_host)
+
+    e2e_steps = max(20, min(args.steps, 200))
+    for i in range(5):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(5 + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks (max time) ----
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pairs = world * B
+        value = pairs * args.steps / (ms * 1e-3)
+        e2e_value = pairs * e2e_steps / e2e_s
+        flops = 16.0 * B * N * M  # 2*N*M evaluations x 8 FLOP per pair
+        achieved = flops / (sweep_us * 1e-6) / 1e12
+        bwd_bytes = (36 * N + 24 * M) * B
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "global_pairs": pairs, "n_points": N, "m_points": M,
+                       "parallelism": f"batch-sharded x{world}" + (", scalar loss all-reduce (NCCL)" if world > 1 else ""),
+                       "l2": f"inputs rotate over {RING_SETS} distinct resident batches ({RING_SETS * B * (N + M) * 12 / 1e6:.0f} MB > 126 MB L2)",
+                       "launch": "C ABI via ctypes, stream-ordered, no CUDA graph"},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps, "api": "kaolin.metrics.pointcloud.chamfer_distance(p1, p2).sum().backward() (fpsg_b200 shim), pinned host inputs"},
+            "gpu_launches": kernels_per_step * args.steps,
+            "roofline": {"bound": "fp32_fma", "kernel": "chamfer_sweep_kernel<16>", "achieved": achieved, "peak": fp32_peak_tflops,
+                         "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": SWEEP_DRAM_TRAFFIC_BYTES,
+                         "us_per_launch": sweep_us, "algorithmic_flop_per_launch": flops,
+                         "peak_source": f"FFMA micro-kernel in this run (fpsg_probe_fp32_peak) at {probe_mhz:.0f} MHz; MEASURED_PEAKS.json has no FP32 row; "
+                                        f"nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                         "how": "sweep kernel launched alone (fpsg_chamfer_sweep_only) over the same input ring, CUDA events on the launch stream"},
+            "roofline_bwd": {"bound": "hbm", "kernel": "chamfer_bwd_kernel", "achieved": bwd_bytes / (bwd_us * 1e-6) / 1e9, "peak": _hbm_peak(),
+                             "unit": "GB/s", "us_per_launch": bwd_us, "algorithmic_bytes_per_launch": bwd_bytes,
+                             "note": "3.9 MB working set is L2-resident: latency-, not bandwidth-bound (SURVEY.md 8d)"},
+            "clocks": clocks,
+        }
+        line["roofline_bwd"]["frac"] = line["roofline_bwd"]["achieved"] / line["roofline_bwd"]["peak"]
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sec = cpu_formulation_pairs_per_s(sample_pairs=8, iters=3)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                    "sample": f"8 of the 32 pairs, best of 3 iterations ({sec:.2f} s each), pure-PyTorch difference-form "
+                                              f"Chamfer fwd+bwd (oracle/torch_formulation.py; Kaolin 0.9.0 is absent), os.cpu_count()={os.cpu_count()}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0  # the profiling recipe's fallback
+
+
+if __name__ == "__main__":
+    main()

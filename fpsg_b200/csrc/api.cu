@@ -19,7 +19,8 @@ int fail(int code, const char* fmt, ...) {
 // implemented in chamfer_fwd.cu / chamfer_bwd.cu / knn.cu
 size_t chamfer_forward_workspace(int B, int N, int M);
 int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
-                           int64_t* idx2, float* loss, float w1, float w2, void* ws, size_t ws_bytes, cudaStream_t stream);
+                           int64_t* idx2, float* loss, float w1, float w2, void* ws, size_t ws_bytes, cudaStream_t stream,
+                           bool sweep_only);
 int chamfer_backward_launch(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2, const float* g1,
                             const float* g2, bool uniform, float w1, float w2, int B, int N, int M, float* gp1, float* gp2,
                             cudaStream_t stream);
@@ -68,7 +69,13 @@ int fpsg_chamfer_fwd(const float* p1, const float* p2, int B, int N, int M, floa
                      int64_t* idx2, void* ws, size_t ws_bytes, fpsg_stream_t stream) {
     if (B > 0 && (!dist1 || !dist2)) return fail(FPSG_EINVAL, "chamfer_fwd: null dist1/dist2");
     return chamfer_forward_launch(p1, p2, B, N, M, dist1, dist2, idx1, idx2, nullptr, 1.f, 1.f, ws, ws_bytes,
-                                  static_cast<cudaStream_t>(stream));
+                                  static_cast<cudaStream_t>(stream), false);
+}
+
+int fpsg_chamfer_sweep_only(const float* p1, const float* p2, int B, int N, int M, void* ws, size_t ws_bytes,
+                            fpsg_stream_t stream) {
+    return chamfer_forward_launch(p1, p2, B, N, M, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 1.f, ws, ws_bytes,
+                                  static_cast<cudaStream_t>(stream), true);
 }
 
 size_t fpsg_chamfer_bwd_workspace_bytes(int, int, int) { return 0; }
@@ -84,7 +91,7 @@ int fpsg_chamfer_loss_fwd(const float* p1, const float* p2, int B, int N, int M,
                           fpsg_stream_t stream) {
     if (B > 0 && !loss) return fail(FPSG_EINVAL, "chamfer_loss_fwd: null loss");
     return chamfer_forward_launch(p1, p2, B, N, M, dist1, dist2, idx1, idx2, loss, w1, w2, ws, ws_bytes,
-                                  static_cast<cudaStream_t>(stream));
+                                  static_cast<cudaStream_t>(stream), false);
 }
 
 int fpsg_chamfer_loss_bwd(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2, const float* gloss,

@@ -452,12 +452,14 @@ chamfer_loss_kernel(const double* __restrict__ losspart, int nrb, int ncb, int N
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
+// sweep_only: launch just the sweep kernel (partials land in the workspace); bench.py times the dominant kernel
+// alone this way for the roofline line.
 int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M, float* dist1, float* dist2,
                            int64_t* idx1, int64_t* idx2, float* loss, float w1, float w2, void* ws, size_t ws_bytes,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, bool sweep_only) {
     if (B < 0 || N < 1 || M < 1) return fail(FPSG_EINVAL, "chamfer: need B >= 0, N >= 1, M >= 1 (got B=%d N=%d M=%d)", B, N, M);
     if (B == 0) return FPSG_OK;
-    if (!p1 || !p2 || !idx1 || !idx2) return fail(FPSG_EINVAL, "chamfer: null p1/p2/idx1/idx2");
+    if (!p1 || !p2 || (!sweep_only && (!idx1 || !idx2))) return fail(FPSG_EINVAL, "chamfer: null p1/p2/idx1/idx2");
     if (B > 65535) return fail(FPSG_EINVAL, "chamfer: B > 65535 not supported in one call");
     if ((long long)N * 3 > 0x7fffffffLL || (long long)M * 3 > 0x7fffffffLL) return fail(FPSG_EINVAL, "chamfer: cloud too large");
     const ChamferPlan pl = make_chamfer_plan(B, N, M);
@@ -484,6 +486,7 @@ int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M
             break;
     }
     FPSG_CUDA_OK(cudaGetLastError());
+    if (sweep_only) return FPSG_OK;
     const FinalizeArgs fa{p1, p2, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rpval, rpsub, colpart,
                           dist1, dist2, idx1, idx2, losspart, pl.nrb, pl.ncb};
     const dim3 fgrid((unsigned)(pl.nrb + pl.ncb), (unsigned)B);

@@ -77,6 +77,12 @@ size_t fpsg_knn_workspace_bytes(int B, int C, int N, int k);
 int fpsg_knn_fwd(const float* x, int B, int C, int N, int k, int64_t* idx, void* ws, size_t ws_bytes,
                  fpsg_stream_t stream);
 
+/* ---- Profiling hooks (used by bench.py for the roofline line; not part of the reference-facing surface) ---- */
+/* Launches only K1's sweep kernel (the dominant kernel) with the workspace of fpsg_chamfer_fwd; the partial
+ * minima stay in the workspace and no output tensor is written. */
+int fpsg_chamfer_sweep_only(const float* p1, const float* p2, int B, int N, int M, void* ws, size_t ws_bytes,
+                            fpsg_stream_t stream);
+
 /* ---- Roofline probe -------------------------------------------------------------------------------------- */
 /* Runs a dependent-free FFMA chain on every SM and returns the achieved FP32 rate in TFLOP/s (2 FLOP per
  * FFMA per lane) through *tflops_host; synchronises `stream`. Used by bench.py as the measured FP32 peak. */
