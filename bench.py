@@ -137,16 +137,25 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import torch
-    sample = 8
     t_all0 = time.perf_counter()
-    rates = []
     torch.set_num_threads(os.cpu_count() or 1)
     from oracle import torch_formulation as TF
+
+    def run(p1, p2):
+        a = p1.clone().requires_grad_(True)
+        TF.chamfer_distance_torch(a, p2, chunk=4).sum().backward()
+
+    # size the per-step sample (1..8 of the 32 pairs) so that warmup + steps finish in about a minute
+    probe1, probe2 = make_inputs(4, N_PTS, M_PTS, seed=1234 + 1)
+    run(probe1, probe2)
+    t0 = time.perf_counter()
+    run(probe1, probe2)
+    per_pair = (time.perf_counter() - t0) / 4
+    sample = int(max(1, min(8, 60.0 / ((args.steps + args.warmup) * per_pair))))
     p1, p2 = make_inputs(sample, N_PTS, M_PTS, seed=1234 + 1)
 
     def step():
-        a = p1.clone().requires_grad_(True)
-        TF.chamfer_distance_torch(a, p2, chunk=4).sum().backward()
+        run(p1, p2)
 
     for _ in range(max(args.warmup, 1)):
         step()
@@ -155,12 +164,11 @@ def run_reference_arm(args):
         step()
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    rates.append(value)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "each step is a bounded sample of 8 of the 32 pairs; value = pairs/s"},
+        "config": {"workload": WORKLOAD, "note": f"each step is a bounded sample of {sample} of the 32 pairs; value = pairs/s"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample} pairs x {args.steps} steps of the c1 workload, pure-PyTorch difference-form Chamfer fwd+bwd "
                                    f"(oracle/torch_formulation.py; Kaolin 0.9.0 itself is absent), os.cpu_count()={os.cpu_count()}"},

@@ -47,6 +47,7 @@ chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
     __shared__ int sWarp[kBwdThreads / 32];
     __shared__ int sList[kBwdChunk];
 
+    cudaGridDependencySynchronize();  // launched with PDL: the forward's outputs are complete from here on
     const bool first = (int)blockIdx.x < s1.blocks;
     const BwdSide& S = first ? s1 : s2;
     const int blk = first ? blockIdx.x : blockIdx.x - s1.blocks;
@@ -156,8 +157,7 @@ int chamfer_backward_launch(const float* p1, const float* p2, const int64_t* idx
     BwdSide s1{p1, p2, idx1, idx2, g1, g2, w1, w2, (float)N, (float)M, gp1, N, M, gp1 ? cdiv(N, kBwdThreads) : 0};
     BwdSide s2{p2, p1, idx2, idx1, g2, g1, w2, w1, (float)M, (float)N, gp2, M, N, gp2 ? cdiv(M, kBwdThreads) : 0};
     const dim3 grid((unsigned)(s1.blocks + s2.blocks), (unsigned)B);
-    chamfer_bwd_kernel<<<grid, kBwdThreads, 0, stream>>>(s1, s2, uniform);
-    FPSG_CUDA_OK(cudaGetLastError());
+    FPSG_CUDA_OK(launch_pdl(chamfer_bwd_kernel, grid, dim3(kBwdThreads), 0, stream, s1, s2, uniform));
     return FPSG_OK;
 }
 

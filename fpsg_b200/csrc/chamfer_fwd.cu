@@ -10,8 +10,8 @@
 //                     units of (pair, row strip, 16 columns) and every CTA takes an equal contiguous run of
 //                     units, so all SMs finish together whatever B, N, M are. CTA = 128 threads; thread t keeps R
 //                     consecutive rows (p1 points) in registers and streams <=64-column sub-blocks of p2
-//                     through shared memory (AoS, three broadcast LDS.128 per 4 columns; the next sub-block is
-//                     prefetched into registers during the current one).
+//                     through a per-warp shared-memory tile (AoS, three broadcast LDS.128 per 4 columns; the next
+//                     sub-block is prefetched into registers during the current one; no CTA-wide barrier).
 //                     Row direction : best[k] = min3(best[k], d, d') -- value only; once per sub-block the
 //                                     thread notes (in shared memory) which sub-block last lowered best[k].
 //                     Column direction: per column the thread's minimum over its R rows, then one warp-wide
@@ -24,8 +24,9 @@
 //                     the winning thread for a column) with the same FP32 instruction sequence, taking the
 //                     lowest index whose distance equals the minimum bit-for-bit. That reproduces the
 //                     reference's strict-'<' ascending scan (lowest index wins ties).
-//   loss kernel     : optional, w1*mean(dist1) + w2*mean(dist2) per pair from per-CTA partial sums (fixed
-//                     order, double) -- the reduction glue of few_shot.py:110 / kaolin's chamfer_distance.
+//   loss (optional) : w1*mean(dist1) + w2*mean(dist2) per pair -- the reduction glue of few_shot.py:110 / kaolin's
+//                     chamfer_distance -- folded into the finalize kernel: per-CTA double sums, added in index
+//                     order by whichever CTA of the pair arrives last (deterministic, no extra launch).
 //
 // Out-of-range rows and columns of ragged tiles are filled with +INF coordinates: their distances are +INF,
 // never win a strict comparison, and never equal a finite minimum.
@@ -40,7 +41,7 @@ typedef unsigned long long u64;
 constexpr int kSweepThreads = 128;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kUnit = 16;           // columns per scheduling unit
-constexpr int kSub = 64;            // columns per shared-memory sub-block (4 units)
+constexpr int kSub = 32;            // columns per shared-memory sub-block (2 units)
 constexpr int kFinThreads = 256;
 
 struct ChamferPlan {
@@ -54,7 +55,7 @@ struct ChamferPlan {
     int maxslots;     // most CTAs that can intersect one (pair, strip)
     int Mpad;         // M rounded up to a unit
     int nrb, ncb;     // finalize CTAs per pair: row blocks, column blocks
-    size_t rpval_off, rpsub_off, colpart_off, losspart_off, total_bytes;
+    size_t rowpart_off, colpart_off, losspart_off, counters_off, total_bytes;
 };
 
 static int g_sm_count = 0;
@@ -95,7 +96,9 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     p.units = (long long)B * p.strips * p.ups;
     const int per_sm = p.R >= 16 ? 4 : 6;
     long long g = (long long)sm_count() * per_sm;
-    if (g > p.units) g = p.units;
+    // at least 4 units per CTA: every CTA that touches a (pair, strip) leaves one row partial per row for the
+    // finalize kernel to merge, and small problems do not need the whole chip anyway
+    if (g > p.units / 4) g = p.units / 4;
     if (g < 1) g = 1;
     p.grid = (int)g;
     p.q = (int)(p.units / g);
@@ -105,14 +108,14 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     p.ncb = cdiv(M, kFinThreads);
     size_t off = 0;
     const size_t rows = (size_t)B * p.strips * p.maxslots * p.TN;
-    p.rpval_off = off;
-    off += align_up(rows * sizeof(float), 256);
-    p.rpsub_off = off;
-    off += align_up(rows * sizeof(int), 256);
+    p.rowpart_off = off;
+    off += align_up(rows * sizeof(u64), 256);
     p.colpart_off = off;
     off += align_up((size_t)B * p.strips * kSweepWarps * p.Mpad * sizeof(u64), 256);
     p.losspart_off = off;
     off += align_up((size_t)B * (p.nrb + p.ncb) * sizeof(double), 256);
+    p.counters_off = off;
+    off += align_up((size_t)B * sizeof(unsigned), 256);
     p.total_bytes = off;
     return p;
 }
@@ -121,9 +124,11 @@ struct SweepArgs {
     const float* p1;
     const float* p2;
     int N, M, strips, ups, q, r, maxslots, Mpad;
-    float* rpval;   // [B*strips][maxslots][TN]   row partial minima
-    int* rpsub;     // [B*strips][maxslots][TN]   sub-block (64 columns) that produced them
+    u64* rowpart;   // [B*strips][maxslots][TN]   (row partial minimum bits << 32) | sub-block that produced it;
+                    //                            one slot per CTA that covered the (pair, strip)
     u64* colpart;   // [B*strips][4 warps][Mpad]  (min bits << 32) | ballot of lanes attaining it
+    unsigned* counters;  // [B] arrival counters of the finalize kernel's loss reduction; zeroed here (or nullptr)
+    int B;
 };
 
 // which CTA owns unit u under the q/r partition
@@ -143,12 +148,14 @@ __device__ __forceinline__ float warp_min_f32(float v) {
 // ---------------------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(kSweepThreads, (R >= 16 ? 4 : 6)) chamfer_sweep_kernel(const SweepArgs a) {
-    // column tile, AoS xyz, double buffered; always written in full (INF beyond the piece), so the 4-column
-    // vector loads of a ragged tail read +INF coordinates
-    __shared__ __align__(16) float sCols[2][kSub * 3];
+    // Every warp keeps its own copy of the current column tile (AoS xyz, 64 columns = 768 B), so the warps of a CTA
+    // never wait for each other: there is no __syncthreads in this kernel. The tile is always written in full
+    // (+INF beyond the piece), so the 4-column vector loads of a ragged tail read +INF coordinates.
+    __shared__ __align__(16) float sCols[kSweepWarps][kSub * 3];
     __shared__ __align__(16) u64 sColRes[kSweepWarps][kSub];
     __shared__ float sPrev[R][kSweepThreads];  // best[k] as of the previous sub-block (thread-private slots)
     __shared__ int sSubIdx[R][kSweepThreads];  // sub-block that last lowered best[k]
+    constexpr int kPf = kSub * 3 / 32;         // prefetch registers per lane (6)
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = blockIdx.x;
@@ -156,18 +163,20 @@ __global__ void __launch_bounds__(kSweepThreads, (R >= 16 ? 4 : 6)) chamfer_swee
     const int uend = u + a.q + (g < a.r ? 1 : 0);
 
     float px[R], py[R], pz[R], best[R];
-    int cur_bs = -1;   // (pair, strip) whose rows are in registers
+    int cur_bs = -1;  // (pair, strip) whose rows are in registers
     int slot = 0;
+    float pf[kPf];    // the next piece's tile, in flight from global memory during the current piece
 
-    // prefetch registers for the next sub-block's tile (<= 192 floats over 128 threads)
-    float pf0 = CUDART_INF_F, pf1 = CUDART_INF_F;
-    int buf = 0;
+    if (g == 0 && a.counters)
+        for (int q = tid; q < a.B; q += kSweepThreads) a.counters[q] = 0u;
+    // let the finalize grid be scheduled onto SMs as this grid's CTAs retire (it waits for our completion itself)
+    cudaTriggerProgrammaticLaunchCompletion();
 
     // describes the sub-block piece starting at unit uu: its (pair,strip), column range, and the unit after it
     auto piece = [&](int uu, int& bs, int& cbeg, int& cend, int& unext) {
         bs = uu / a.ups;
         const int cu = uu - bs * a.ups;
-        int e = uu - (cu & 3) + 4;              // end of the 64-column sub-block
+        int e = uu - (cu % (kSub / kUnit)) + kSub / kUnit;  // end of the sub-block
         const int seg_end = (bs + 1) * a.ups;  // end of the (pair, strip)
         e = e < seg_end ? e : seg_end;
         e = e < uend ? e : uend;
@@ -176,51 +185,66 @@ __global__ void __launch_bounds__(kSweepThreads, (R >= 16 ? 4 : 6)) chamfer_swee
         cend = min(a.M, (cu + (e - uu)) * kUnit);
     };
     auto fetch = [&](int uu) {  // global -> registers; INF beyond the piece so padded columns never win
-        int bs, un;
-        int cb, ce;
+        int bs, un, cb, ce;
         piece(uu, bs, cb, ce, un);
         const float* src = a.p2 + ((size_t)(bs / a.strips) * a.M + cb) * 3;
         const int n = (ce - cb) * 3;
-        pf0 = tid < n ? __ldg(src + tid) : CUDART_INF_F;
-        pf1 = tid + kSweepThreads < n ? __ldg(src + tid + kSweepThreads) : CUDART_INF_F;
+#pragma unroll
+        for (int q = 0; q < kPf; ++q) pf[q] = lane + 32 * q < n ? __ldg(src + lane + 32 * q) : CUDART_INF_F;
     };
 
     if (u < uend) fetch(u);
 
     while (u < uend) {
-        int bs, unext;
-        int cbeg, cend;
+        int bs, unext, cbeg, cend;
         piece(u, bs, cbeg, cend, unext);
         const int b = bs / a.strips, strip = bs % a.strips;
 
-        // park the prefetched tile in shared memory
-        sCols[buf][tid] = pf0;
-        if (tid + kSweepThreads < kSub * 3) sCols[buf][tid + kSweepThreads] = pf1;
+        // park the prefetched tile in this warp's shared-memory buffer
+        __syncwarp();  // all lanes are done reading the previous tile
+#pragma unroll
+        for (int q = 0; q < kPf; ++q) sCols[w][lane + 32 * q] = pf[q];
 
         if (bs != cur_bs) {
-            // new (pair, strip): bring this thread's R rows into registers
+            // new (pair, strip): bring this thread's R consecutive rows into registers
             cur_bs = bs;
             slot = g - cta_of_unit(bs * a.ups, a.q, a.r);
             const float* p1b = a.p1 + (size_t)b * a.N * 3;
             const int row0 = strip * (kSweepThreads * R) + tid * R;
+            const float* rsrc = p1b + 3 * (size_t)row0;
+            if (row0 + R <= a.N && (reinterpret_cast<uintptr_t>(rsrc) & 15) == 0) {
+                float4 v[3 * R / 4];
+#pragma unroll
+                for (int q = 0; q < 3 * R / 4; ++q) v[q] = __ldg(reinterpret_cast<const float4*>(rsrc) + q);
+                const float* f = reinterpret_cast<const float*>(v);
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    px[k] = f[3 * k];
+                    py[k] = f[3 * k + 1];
+                    pz[k] = f[3 * k + 2];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const bool ok = row0 + k < a.N;
+                    px[k] = ok ? __ldg(rsrc + 3 * k) : CUDART_INF_F;
+                    py[k] = ok ? __ldg(rsrc + 3 * k + 1) : CUDART_INF_F;
+                    pz[k] = ok ? __ldg(rsrc + 3 * k + 2) : CUDART_INF_F;
+                }
+            }
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                const int rr = row0 + k;
-                const bool ok = rr < a.N;
-                px[k] = ok ? __ldg(p1b + 3 * rr) : CUDART_INF_F;
-                py[k] = ok ? __ldg(p1b + 3 * rr + 1) : CUDART_INF_F;
-                pz[k] = ok ? __ldg(p1b + 3 * rr + 2) : CUDART_INF_F;
                 best[k] = CUDART_INF_F;
                 sPrev[k][tid] = CUDART_INF_F;
                 sSubIdx[k][tid] = cbeg / kSub;
             }
         }
-        __syncthreads();  // tile visible to all warps (and the other buffer is free again)
+        __syncwarp();  // tile visible to the whole warp
         if (unext < uend) fetch(unext);  // overlaps the whole sub-block below
 
         const int ncols = cend - cbeg;
         const int nsteps = (ncols + 3) >> 2;
-        const float* tile = sCols[buf];
+        const float* tile = sCols[w];
         u64* res = sColRes[w];
 #pragma unroll 1
         for (int step = 0; step < nsteps; ++step) {
@@ -276,24 +300,20 @@ __global__ void __launch_bounds__(kSweepThreads, (R >= 16 ? 4 : 6)) chamfer_swee
             u64* dst = a.colpart + (((size_t)bs * kSweepWarps + w) * a.Mpad + cbeg);
             for (int c = lane; c < ncols; c += 32) dst[c] = res[c];
         }
-        __syncwarp();
 
         // last piece of this (pair, strip) for this CTA: flush the row partials
         {
             int nbs = -1;
             if (unext < uend) nbs = unext / a.ups;
             if (nbs != bs) {
-                const size_t base = ((size_t)bs * a.maxslots + slot) * (kSweepThreads * R) + tid * R;
+                ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.rowpart + ((size_t)bs * a.maxslots + slot) * (kSweepThreads * R) + tid * R);
 #pragma unroll
-                for (int k = 0; k < R; k += 4) {
-                    *reinterpret_cast<float4*>(a.rpval + base + k) = make_float4(best[k], best[k + 1], best[k + 2], best[k + 3]);
-                    *reinterpret_cast<int4*>(a.rpsub + base + k) =
-                        make_int4(sSubIdx[k][tid], sSubIdx[k + 1][tid], sSubIdx[k + 2][tid], sSubIdx[k + 3][tid]);
-                }
+                for (int k = 0; k < R; k += 2)
+                    dst[k >> 1] = make_ulonglong2(((u64)__float_as_uint(best[k]) << 32) | (unsigned)sSubIdx[k][tid],
+                                                  ((u64)__float_as_uint(best[k + 1]) << 32) | (unsigned)sSubIdx[k + 1][tid]);
             }
         }
         u = unext;
-        buf ^= 1;
     }
 }
 
@@ -304,19 +324,26 @@ struct FinalizeArgs {
     const float* p1;
     const float* p2;
     int N, M, R, strips, ups, q, r, maxslots, Mpad;
-    const float* rpval;
-    const int* rpsub;
+    const u64* rowpart;
     const u64* colpart;
     float* dist1;
     float* dist2;
     int64_t* idx1;
     int64_t* idx2;
-    double* losspart;
+    double* losspart;    // per-CTA sums of the distances (nullptr: no loss wanted)
+    unsigned* counters;  // per-pair arrival counters, zeroed by the sweep kernel
+    float* loss;
+    float w1, w2;
     int nrb, ncb;
+    int dbg;  // experiment switches (FPSG_FIN_DBG), 0 in production
 };
 
 __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const FinalizeArgs a) {
+    __shared__ __align__(16) float4 sPt[kFinThreads];  // (x, y, z, minimum) of the thread's point
+    __shared__ int sBase[kFinThreads];                  // first candidate index to re-evaluate
+    __shared__ int sFound[kFinThreads];
     __shared__ double sRed[kFinThreads / 32];
+    __shared__ bool sLast;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int b = blockIdx.y, blk = blockIdx.x;
@@ -324,6 +351,12 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
     const float* __restrict__ p2b = a.p2 + (size_t)b * a.M * 3;
     const int TN = kSweepThreads * a.R;
     float mine = 0.f;  // this thread's distance, for the loss partial
+    cudaTriggerProgrammaticLaunchCompletion();  // a following backward may start to launch
+    cudaGridDependencySynchronize();            // the sweep's partials are complete and visible from here on
+    if (a.dbg) sFound[tid] = 0;
+    if (a.dbg & 16) return;
+    if ((a.dbg & 32) && blk < a.nrb) return;
+    if ((a.dbg & 64) && blk >= a.nrb) return;
 
     if (blk < a.nrb) {
         // ---- rows: each thread merges the partials of the CTAs that covered its row's strip ... ----
@@ -336,38 +369,70 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
             const int bs = b * a.strips + strip;
             const int u0 = bs * a.ups;
             const int g0 = cta_of_unit(u0, a.q, a.r), g1 = cta_of_unit(u0 + a.ups - 1, a.q, a.r);
-            for (int s = 0; s <= g1 - g0; ++s) {  // ascending slot = ascending columns: strict '<' keeps the lowest
-                const size_t o = ((size_t)bs * a.maxslots + s) * TN + within;
-                const float v = a.rpval[o];
-                if (v < m) {
-                    m = v;
-                    sub = a.rpsub[o];
-                }
+            // the keys order by (minimum, sub-block): their u64 minimum is the reference's strict-'<' ascending scan.
+            // All loads of the merge are issued together (one L2 round trip); slots past nsl hold stale data.
+            const u64* rp = a.rowpart + (size_t)bs * a.maxslots * TN + within;
+            const int nsl = g1 - g0 + 1;
+            u64 key = ~0ull;
+            constexpr int kSlotBatch = 12;  // loads in flight together
+            for (int s0 = 0; s0 < nsl; s0 += kSlotBatch) {
+                u64 v[kSlotBatch];
+#pragma unroll
+                for (int s = 0; s < kSlotBatch; ++s) v[s] = s0 + s < nsl ? rp[(size_t)(s0 + s) * TN] : ~0ull;
+#pragma unroll
+                for (int s = 0; s < kSlotBatch; ++s) key = v[s] < key ? v[s] : key;
             }
+            m = __uint_as_float((unsigned)(key >> 32));
+            sub = (int)(unsigned)key;
             ax = __ldg(p1b + 3 * i);
             ay = __ldg(p1b + 3 * i + 1);
             az = __ldg(p1b + 3 * i + 2);
             mine = m;
         }
-        // ... then the warp scans the 64 columns of every row's winning sub-block together: two coalesced columns
-        // per lane, and the lowest lane whose distance equals the minimum gives the arg-min
-        int found = 0;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-            const float mm = __shfl_sync(0xffffffffu, m, rr);
-            const int j0 = __shfl_sync(0xffffffffu, sub, rr) * kSub;
-            const float bx = __shfl_sync(0xffffffffu, ax, rr), by = __shfl_sync(0xffffffffu, ay, rr), bz = __shfl_sync(0xffffffffu, az, rr);
-            const int ja = j0 + lane, jb = j0 + 32 + lane;
-            float da = CUDART_INF_F, db = CUDART_INF_F;
-            if (ja < a.M) da = sqdist(bx, by, bz, __ldg(p2b + 3 * ja), __ldg(p2b + 3 * ja + 1), __ldg(p2b + 3 * ja + 2));
-            if (jb < a.M) db = sqdist(bx, by, bz, __ldg(p2b + 3 * jb), __ldg(p2b + 3 * jb + 1), __ldg(p2b + 3 * jb + 2));
-            const unsigned ha = __ballot_sync(0xffffffffu, da == mm), hb = __ballot_sync(0xffffffffu, db == mm);
-            const int f = ha ? j0 + __ffs(ha) - 1 : (hb ? j0 + 32 + __ffs(hb) - 1 : j0);
-            if (lane == rr) found = f;
+        sPt[tid] = make_float4(ax, ay, az, m);
+        sBase[tid] = sub * kSub;
+        __syncwarp();
+        // ... then the warp re-evaluates the kSub columns of every row's winning sub-block together (coalesced);
+        // the lowest lane whose distance equals the minimum bit-for-bit is the arg-min. Lanes past the end of the
+        // cloud re-evaluate the last column: they can only tie with a lower lane that holds the same column.
+        const int last = a.M - 1;
+        constexpr int kBatch = 8;  // rows whose candidate loads are put in flight together (the loop is latency-bound)
+        constexpr int kH = kSub / 32;
+        for (int rb = 0; rb < ((a.dbg & 1) ? 0 : 32); rb += kBatch) {
+            float cx[kBatch][kH], cy[kBatch][kH], cz[kBatch][kH];
+#pragma unroll
+            for (int r = 0; r < kBatch; ++r) {
+                const int j0 = sBase[w * 32 + rb + r];
+#pragma unroll
+                for (int h = 0; h < kH; ++h) {
+                    const int j = min(j0 + 32 * h + lane, last);
+                    cx[r][h] = __ldg(p2b + 3 * j);
+                    cy[r][h] = __ldg(p2b + 3 * j + 1);
+                    cz[r][h] = __ldg(p2b + 3 * j + 2);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kBatch; ++r) {
+                const float4 pt = sPt[w * 32 + rb + r];
+                const int j0 = sBase[w * 32 + rb + r];
+                int f = j0;
+                bool done = false;
+#pragma unroll
+                for (int h = 0; h < kH; ++h) {
+                    const float d = sqdist(pt.x, pt.y, pt.z, cx[r][h], cy[r][h], cz[r][h]);
+                    const unsigned hit = __ballot_sync(0xffffffffu, d == pt.w);
+                    if (hit && !done) {
+                        f = j0 + 32 * h + __ffs(hit) - 1;
+                        done = true;
+                    }
+                }
+                if (lane == 0) sFound[w * 32 + rb + r] = f;
+            }
         }
-        if (valid) {
+        __syncwarp();
+        if (valid && !(a.dbg & 256)) {
             if (a.dist1) a.dist1[(size_t)b * a.N + i] = m;
-            a.idx1[(size_t)b * a.N + i] = found;
+            a.idx1[(size_t)b * a.N + i] = sFound[tid];
         }
     } else {
         // ---- columns: each thread merges strips x warps ... ----
@@ -377,6 +442,7 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
         int r0 = 0;
         if (valid) {
             for (int s = 0; s < a.strips; ++s) {
+#pragma unroll
                 for (int ww = 0; ww < kSweepWarps; ++ww) {  // ascending (strip, warp) = ascending rows
                     const u64 rec = a.colpart[(((size_t)b * a.strips + s) * kSweepWarps + ww) * a.Mpad + j];
                     const float v = __uint_as_float((unsigned)(rec >> 32));
@@ -391,62 +457,72 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
             qz = __ldg(p2b + 3 * j + 2);
             mine = m;
         }
-        // ... then groups of R lanes scan the R consecutive rows of each column's winning thread (coalesced)
+        sPt[tid] = make_float4(qx, qy, qz, m);
+        sBase[tid] = r0;
+        __syncwarp();
+        // ... then groups of R lanes re-evaluate the R consecutive rows of each column's winning thread (coalesced)
         const int R = a.R, per = 32 / R, grp = lane / R, off = lane - grp * R;
-        const unsigned gmask = (R == 32 ? 0xffffffffu : ((1u << R) - 1u)) << (grp * R);
-        int found = 0;
-        for (int it = 0; it < R; ++it) {
-            const int src = it * per + grp;  // the lane whose column this group scans now
-            const float mm = __shfl_sync(0xffffffffu, m, src);
-            const int rr0 = __shfl_sync(0xffffffffu, r0, src);
-            const float cx = __shfl_sync(0xffffffffu, qx, src), cy = __shfl_sync(0xffffffffu, qy, src), cz = __shfl_sync(0xffffffffu, qz, src);
-            const int r = rr0 + off;
-            float d = CUDART_INF_F;
-            if (r < a.N) d = sqdist(cx, cy, cz, __ldg(p1b + 3 * r), __ldg(p1b + 3 * r + 1), __ldg(p1b + 3 * r + 2));
-            const unsigned hit = __ballot_sync(0xffffffffu, d == mm) & gmask;
-            int f = hit ? rr0 + (__ffs(hit) - 1 - grp * R) : rr0;
-            if (f >= a.N) f = 0;
-            // hand the group's answer to the lane that owns the column
-            const int want = lane - it * per;  // group index that worked for this lane's column, if in [0, per)
-            const int fo = __shfl_sync(0xffffffffu, f, (want * R) & 31);
-            if (want >= 0 && want < per) found = fo;
+        const unsigned gmask = ((1u << R) - 1u) << (grp * R);  // R <= 16
+        const int last = a.N - 1;
+        constexpr int kCB = 4;  // iterations whose candidate loads are in flight together (R is a multiple of 4)
+        for (int ib = 0; ib < ((a.dbg & 2) ? 0 : R); ib += kCB) {
+            float rx[kCB], ry[kCB], rz[kCB];
+#pragma unroll
+            for (int t = 0; t < kCB; ++t) {
+                const int c = w * 32 + (ib + t) * per + grp;  // the column this group of lanes serves in iteration ib+t
+                const int r = min(sBase[c] + off, last);
+                rx[t] = __ldg(p1b + 3 * r);
+                ry[t] = __ldg(p1b + 3 * r + 1);
+                rz[t] = __ldg(p1b + 3 * r + 2);
+            }
+#pragma unroll
+            for (int t = 0; t < kCB; ++t) {
+                const int c = w * 32 + (ib + t) * per + grp;
+                const float4 pt = sPt[c];
+                const int rr0 = sBase[c];
+                const float d = sqdist(pt.x, pt.y, pt.z, rx[t], ry[t], rz[t]);
+                const unsigned hit = __ballot_sync(0xffffffffu, d == pt.w) & gmask;
+                if (off == 0) sFound[c] = hit ? min(rr0 + (__ffs(hit) - 1 - grp * R), last) : min(rr0, last);
+            }
         }
+        __syncwarp();
         if (valid) {
             if (a.dist2) a.dist2[(size_t)b * a.M + j] = m;
-            a.idx2[(size_t)b * a.M + j] = found;
+            a.idx2[(size_t)b * a.M + j] = sFound[tid];
         }
     }
 
-    if (a.losspart) {
-        // fixed-order block sum in double: lanes by shuffle tree, warps in ascending order
+    if (a.losspart && !(a.dbg & 4)) {
+        // fixed-order block sum in double (lanes by shuffle tree, warps ascending); the last CTA of the pair to
+        // arrive adds the per-CTA sums in index order, so the result does not depend on arrival order
         double v = (double)mine;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) sRed[w] = v;
         __syncthreads();
+        const int nblk = a.nrb + a.ncb;
         if (tid == 0) {
             double s = 0.0;
             for (int q = 0; q < kFinThreads / 32; ++q) s += sRed[q];
-            a.losspart[(size_t)b * (a.nrb + a.ncb) + blk] = s;
+            a.losspart[(size_t)b * nblk + blk] = s;
+            __threadfence();
+            sLast = atomicAdd(a.counters + b, 1u) == (unsigned)(nblk - 1);
+        }
+        __syncthreads();
+        if (sLast && w == 0) {
+            __threadfence();
+            const volatile double* lp = a.losspart + (size_t)b * nblk;
+            double s1 = 0.0, s2 = 0.0;
+            for (int q = lane; q < a.nrb; q += 32) s1 += lp[q];
+            for (int q = lane; q < a.ncb; q += 32) s2 += lp[a.nrb + q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_down_sync(0xffffffffu, s1, o);
+                s2 += __shfl_down_sync(0xffffffffu, s2, o);
+            }
+            if (lane == 0) a.loss[b] = (float)((double)a.w1 * (s1 / a.N) + (double)a.w2 * (s2 / a.M));
         }
     }
-}
-
-// loss[b] = w1 * mean(dist1[b]) + w2 * mean(dist2[b]) from the finalize CTAs' partial sums
-__global__ void __launch_bounds__(32)
-chamfer_loss_kernel(const double* __restrict__ losspart, int nrb, int ncb, int N, int M, float w1, float w2,
-                    float* __restrict__ loss) {
-    const int b = blockIdx.x, lane = threadIdx.x;
-    const double* lp = losspart + (size_t)b * (nrb + ncb);
-    double s1 = 0.0, s2 = 0.0;
-    for (int q = lane; q < nrb; q += 32) s1 += lp[q];
-    for (int q = lane; q < ncb; q += 32) s2 += lp[nrb + q];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_down_sync(0xffffffffu, s1, o);
-        s2 += __shfl_down_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) loss[b] = (float)((double)w1 * (s1 / N) + (double)w2 * (s2 / M));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -468,12 +544,12 @@ int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M
         return fail(FPSG_EWORKSPACE, "chamfer: workspace of %zu bytes required, %zu given", pl.total_bytes, ws ? ws_bytes : (size_t)0);
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(FPSG_EWORKSPACE, "chamfer: workspace must be 256-byte aligned");
     char* base = static_cast<char*>(ws);
-    float* rpval = reinterpret_cast<float*>(base + pl.rpval_off);
-    int* rpsub = reinterpret_cast<int*>(base + pl.rpsub_off);
+    u64* rowpart = reinterpret_cast<u64*>(base + pl.rowpart_off);
     u64* colpart = reinterpret_cast<u64*>(base + pl.colpart_off);
     double* losspart = loss ? reinterpret_cast<double*>(base + pl.losspart_off) : nullptr;
+    unsigned* counters = loss ? reinterpret_cast<unsigned*>(base + pl.counters_off) : nullptr;
 
-    const SweepArgs sa{p1, p2, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rpval, rpsub, colpart};
+    const SweepArgs sa{p1, p2, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart, counters, B};
     switch (pl.R) {
         case 16:
             chamfer_sweep_kernel<16><<<pl.grid, kSweepThreads, 0, stream>>>(sa);
@@ -487,15 +563,11 @@ int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M
     }
     FPSG_CUDA_OK(cudaGetLastError());
     if (sweep_only) return FPSG_OK;
-    const FinalizeArgs fa{p1, p2, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rpval, rpsub, colpart,
-                          dist1, dist2, idx1, idx2, losspart, pl.nrb, pl.ncb};
+    const FinalizeArgs fa{p1, p2, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart,
+                          dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb, getenv("FPSG_FIN_DBG") ? atoi(getenv("FPSG_FIN_DBG")) : 0};
     const dim3 fgrid((unsigned)(pl.nrb + pl.ncb), (unsigned)B);
-    chamfer_finalize_kernel<<<fgrid, kFinThreads, 0, stream>>>(fa);
+    if (!(fa.dbg & 8)) FPSG_CUDA_OK(launch_pdl(chamfer_finalize_kernel, fgrid, dim3(kFinThreads), 0, stream, fa));
     FPSG_CUDA_OK(cudaGetLastError());
-    if (loss) {
-        chamfer_loss_kernel<<<B, 32, 0, stream>>>(losspart, pl.nrb, pl.ncb, N, M, w1, w2, loss);
-        FPSG_CUDA_OK(cudaGetLastError());
-    }
     return FPSG_OK;
 }
 

@@ -4,6 +4,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/fpsg_b200.h"
 
 namespace fpsg {
@@ -30,6 +32,23 @@ __device__ __forceinline__ float sqdist(float ax, float ay, float az, float bx, 
     float t = __fmul_rn(dy, dy);
     t = __fmaf_rn(dx, dx, t);
     return __fmaf_rn(dz, dz, t);
+}
+
+// Launch with programmatic stream serialization (PDL): the grid may start while its predecessor in the stream is
+// still draining; the kernel calls cudaGridDependencySynchronize() before it touches the predecessor's output.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 // 3-input FP32 min (FMNMX3 on sm_100a): one ALU-pipe slot for two comparisons.
