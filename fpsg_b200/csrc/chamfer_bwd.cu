@@ -47,7 +47,8 @@ chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
     __shared__ int sWarp[kBwdThreads / 32];
     __shared__ int sList[kBwdChunk];
 
-    cudaGridDependencySynchronize();  // launched with PDL: the forward's outputs are complete from here on
+    cudaTriggerProgrammaticLaunchCompletion();  // a following kernel launched with PDL may start to launch
+    cudaGridDependencySynchronize();            // launched with PDL: the forward's outputs are complete from here on
     const bool first = (int)blockIdx.x < s1.blocks;
     const BwdSide& S = first ? s1 : s2;
     const int blk = first ? blockIdx.x : blockIdx.x - s1.blocks;
@@ -83,13 +84,16 @@ chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
         const int jj = tid + q * kBwdThreads;
         t[q] = jj < S.Nq ? iQ[jj] - i0 : -1;
     }
-    double gx = 0.0, gy = 0.0, gz = 0.0;
+    // the direct edge's other end: its load depends on x, so it is issued here and consumed only after the first
+    // inverted-index build below, which hides its latency
+    float dqx = 0.f, dqy = 0.f, dqz = 0.f, gdir = 0.f;
     if (live) {
-        const float g = uniform ? uA : __fmul_rn(2.0f, __ldg(S.gA + (size_t)b * S.Na + i));
-        gx = (double)__fmul_rn(g, __fsub_rn(ax, __ldg(Qb + 3 * x)));
-        gy = (double)__fmul_rn(g, __fsub_rn(ay, __ldg(Qb + 3 * x + 1)));
-        gz = (double)__fmul_rn(g, __fsub_rn(az, __ldg(Qb + 3 * x + 2)));
+        gdir = uniform ? uA : __fmul_rn(2.0f, __ldg(S.gA + (size_t)b * S.Na + i));
+        dqx = __ldg(Qb + 3 * x);
+        dqy = __ldg(Qb + 3 * x + 1);
+        dqz = __ldg(Qb + 3 * x + 2);
     }
+    double gx = 0.0, gy = 0.0, gz = 0.0;
 
     for (int j0 = 0; j0 < S.Nq; j0 += kBwdChunk) {
         const int jn = min(kBwdChunk, S.Nq - j0);
@@ -127,16 +131,35 @@ chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
         for (int q = 0; q < kPer; ++q)
             if (t[q] >= 0 && t[q] < kBwdThreads) sList[atomicAdd(&sCursor[(int)t[q]], 1)] = j0 + tid + q * kBwdThreads;
         __syncthreads();
-        // gather: this thread's bucket
+        // gather: this thread's bucket, four edges in flight at a time (each is a dependent L2 round trip)
         if (live) {
-            for (int e = start; e < start + c; ++e) {
-                const int j = sList[e];
-                const float g = uniform ? uQ : __fmul_rn(2.0f, __ldg(S.gQ + (size_t)b * S.Nq + j));
-                gx += (double)__fmul_rn(g, __fsub_rn(ax, __ldg(Qb + 3 * j)));
-                gy += (double)__fmul_rn(g, __fsub_rn(ay, __ldg(Qb + 3 * j + 1)));
-                gz += (double)__fmul_rn(g, __fsub_rn(az, __ldg(Qb + 3 * j + 2)));
+            if (j0 == 0) {
+                gx = (double)__fmul_rn(gdir, __fsub_rn(ax, dqx));
+                gy = (double)__fmul_rn(gdir, __fsub_rn(ay, dqy));
+                gz = (double)__fmul_rn(gdir, __fsub_rn(az, dqz));
+            }
+            for (int e = start; e < start + c; e += 4) {
+                float qx[4], qy[4], qz[4], gg[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const bool on = e + v < start + c;
+                    const int j = on ? sList[e + v] : 0;
+                    gg[v] = !on ? 0.f : (uniform ? uQ : __fmul_rn(2.0f, __ldg(S.gQ + (size_t)b * S.Nq + j)));
+                    qx[v] = on ? __ldg(Qb + 3 * j) : ax;
+                    qy[v] = on ? __ldg(Qb + 3 * j + 1) : ay;
+                    qz[v] = on ? __ldg(Qb + 3 * j + 2) : az;
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (e + v < start + c) {
+                        gx += (double)__fmul_rn(gg[v], __fsub_rn(ax, qx[v]));
+                        gy += (double)__fmul_rn(gg[v], __fsub_rn(ay, qy[v]));
+                        gz += (double)__fmul_rn(gg[v], __fsub_rn(az, qz[v]));
+                    }
+                }
             }
         }
+        if (j0 + kBwdChunk >= S.Nq) break;  // uniform: no further chunk reuses the shared arrays
         __syncthreads();
     }
     if (live) {

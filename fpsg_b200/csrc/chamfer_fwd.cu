@@ -44,8 +44,12 @@ constexpr int kUnit = 16;           // columns per scheduling unit
 constexpr int kSub = 32;            // columns per shared-memory sub-block (2 units)
 constexpr int kFinThreads = 256;
 
+// resident sweep CTAs per SM (register-limited): the persistent grid is this times the SM count
+constexpr int sweep_ctas_per_sm(int R, bool packed) { return packed ? 3 : (R >= 16 ? 4 : 6); }
+
 struct ChamferPlan {
     int R;            // rows per thread in the sweep
+    bool packed;      // f32x2 arithmetic variant (R == 16 only)
     int TN;           // rows per strip (kSweepThreads * R)
     int strips;       // row strips per pair
     int ups;          // 16-column units per (pair, strip)
@@ -94,7 +98,9 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     p.ups = cdiv(M, kUnit);
     p.Mpad = p.ups * kUnit;
     p.units = (long long)B * p.strips * p.ups;
-    const int per_sm = p.R >= 16 ? 4 : 6;
+    p.packed = false;
+    if (const char* e = getenv("FPSG_SWEEP_PACKED")) p.packed = atoi(e) != 0 && p.R == 16;  // tuning override
+    const int per_sm = sweep_ctas_per_sm(p.R, p.packed);
     long long g = (long long)sm_count() * per_sm;
     // at least 4 units per CTA: every CTA that touches a (pair, strip) leaves one row partial per row for the
     // finalize kernel to merge, and small problems do not need the whole chip anyway
@@ -146,68 +152,104 @@ __device__ __forceinline__ float warp_min_f32(float v) {
 // ---------------------------------------------------------------------------------------------------------
 // sweep
 // ---------------------------------------------------------------------------------------------------------
-template <int R>
-__global__ void __launch_bounds__(kSweepThreads, (R >= 16 ? 4 : 6)) chamfer_sweep_kernel(const SweepArgs a) {
-    // Every warp keeps its own copy of the current column tile (AoS xyz, 64 columns = 768 B), so the warps of a CTA
-    // never wait for each other: there is no __syncthreads in this kernel. The tile is always written in full
-    // (+INF beyond the piece), so the 4-column vector loads of a ragged tail read +INF coordinates.
-    __shared__ __align__(16) float sCols[kSweepWarps][kSub * 3];
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// packed FP32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a): two IEEE round-to-nearest operations per issue slot,
+// bit-identical to the scalar forms
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// PACKED: the distance arithmetic runs on f32x2 pairs (two rows per instruction); same bits, half the issue slots
+// for the FP32 work, at the price of duplicated column coordinates in registers (3 CTAs/SM instead of 4).
+template <int R, bool PACKED>
+__global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) chamfer_sweep_kernel(const SweepArgs a) {
+    // Every warp keeps its own copy of the current column tile, so the warps of a CTA never wait for each other:
+    // there is no __syncthreads in this kernel. Scalar layout: AoS xyz (kSub*3 floats). Packed layout: every
+    // coordinate twice, [c] -> (x,x,y,y) and [c] -> (z,z), so a 64-bit register pair feeds both halves of an
+    // f32x2 operation. The tile is always written in full (+INF beyond the piece): a ragged tail reads +INF.
+    __shared__ __align__(16) float sCols[kSweepWarps][kSub * (PACKED ? 6 : 3)];
     __shared__ __align__(16) u64 sColRes[kSweepWarps][kSub];
     __shared__ float sPrev[R][kSweepThreads];  // best[k] as of the previous sub-block (thread-private slots)
     __shared__ int sSubIdx[R][kSweepThreads];  // sub-block that last lowered best[k]
-    constexpr int kPf = kSub * 3 / 32;         // prefetch registers per lane (6)
+    constexpr int kPf = kSub * 3 / 32;         // prefetch registers per lane
+    constexpr int kUps = kSub / kUnit;         // units per sub-block
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = blockIdx.x;
-    int u = g * a.q + min(g, a.r);
-    const int uend = u + a.q + (g < a.r ? 1 : 0);
+
+    // this CTA's run of units, walked as pieces: a piece never crosses a sub-block or a (pair, strip) boundary
+    int left = a.q + (g < a.r ? 1 : 0);           // units still to do
+    int bs, cu;                                    // (pair, strip) index and unit inside it
+    {
+        const int u0 = g * a.q + min(g, a.r);
+        bs = u0 / a.ups;
+        cu = u0 - bs * a.ups;
+    }
+    auto piece_units = [&](int cu_, int left_) { return min(min(kUps - (cu_ % kUps), a.ups - cu_), left_); };
 
     float px[R], py[R], pz[R], best[R];
-    int cur_bs = -1;  // (pair, strip) whose rows are in registers
-    int slot = 0;
+    u64 PX[R / 2], PY[R / 2], PZ[R / 2];  // PACKED: rows paired in 64-bit registers, P[k2] = (p[2 k2], p[2 k2 + 1])
+    int cur_bs = -1;                      // (pair, strip) whose rows are in registers
+    int slot = 0, b = 0, strip = 0;
     float pf[kPf];    // the next piece's tile, in flight from global memory during the current piece
 
+    // where this lane's prefetched elements go in the packed tile (element e = lane + 32 q of the AoS stream)
+    int pk_off[kPf];
+#pragma unroll
+    for (int q = 0; q < kPf; ++q) {
+        const int e = lane + 32 * q, c = e / 3, comp = e - 3 * c;
+        pk_off[q] = comp < 2 ? 4 * c + 2 * comp : 4 * kSub + 2 * c;  // floats; XY block first, then Z block
+    }
+
+    cudaGridDependencySynchronize();  // (PDL) the producer of p1/p2 and the previous user of the workspace are done
     if (g == 0 && a.counters)
         for (int q = tid; q < a.B; q += kSweepThreads) a.counters[q] = 0u;
     // let the finalize grid be scheduled onto SMs as this grid's CTAs retire (it waits for our completion itself)
     cudaTriggerProgrammaticLaunchCompletion();
 
-    // describes the sub-block piece starting at unit uu: its (pair,strip), column range, and the unit after it
-    auto piece = [&](int uu, int& bs, int& cbeg, int& cend, int& unext) {
-        bs = uu / a.ups;
-        const int cu = uu - bs * a.ups;
-        int e = uu - (cu % (kSub / kUnit)) + kSub / kUnit;  // end of the sub-block
-        const int seg_end = (bs + 1) * a.ups;  // end of the (pair, strip)
-        e = e < seg_end ? e : seg_end;
-        e = e < uend ? e : uend;
-        unext = e;
-        cbeg = cu * kUnit;
-        cend = min(a.M, (cu + (e - uu)) * kUnit);
-    };
-    auto fetch = [&](int uu) {  // global -> registers; INF beyond the piece so padded columns never win
-        int bs, un, cb, ce;
-        piece(uu, bs, cb, ce, un);
-        const float* src = a.p2 + ((size_t)(bs / a.strips) * a.M + cb) * 3;
-        const int n = (ce - cb) * 3;
+    auto fetch = [&](int bs_, int cu_, int n_) {  // global -> registers; INF beyond the piece: padded columns never win
+        const int b_ = a.strips == 1 ? bs_ : bs_ / a.strips;
+        const int cb = cu_ * kUnit;
+        const int n = (min(a.M, cb + n_ * kUnit) - cb) * 3;
+        const float* src = a.p2 + ((size_t)b_ * a.M + cb) * 3;
 #pragma unroll
         for (int q = 0; q < kPf; ++q) pf[q] = lane + 32 * q < n ? __ldg(src + lane + 32 * q) : CUDART_INF_F;
     };
 
-    if (u < uend) fetch(u);
+    if (left > 0) fetch(bs, cu, piece_units(cu, left));
 
-    while (u < uend) {
-        int bs, unext, cbeg, cend;
-        piece(u, bs, cbeg, cend, unext);
-        const int b = bs / a.strips, strip = bs % a.strips;
+    while (left > 0) {
+        const int nun = piece_units(cu, left);
+        const int cbeg = cu * kUnit;
+        const int cend = min(a.M, cbeg + nun * kUnit);
+        // the piece after this one
+        int nbs = bs, ncu = cu + nun;
+        const int nleft = left - nun;
+        if (ncu == a.ups) {
+            ncu = 0;
+            ++nbs;
+        }
 
         // park the prefetched tile in this warp's shared-memory buffer
         __syncwarp();  // all lanes are done reading the previous tile
+        if (PACKED) {
 #pragma unroll
-        for (int q = 0; q < kPf; ++q) sCols[w][lane + 32 * q] = pf[q];
+            for (int q = 0; q < kPf; ++q) *reinterpret_cast<float2*>(&sCols[w][pk_off[q]]) = make_float2(pf[q], pf[q]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < kPf; ++q) sCols[w][lane + 32 * q] = pf[q];
+        }
 
         if (bs != cur_bs) {
             // new (pair, strip): bring this thread's R consecutive rows into registers
             cur_bs = bs;
+            b = a.strips == 1 ? bs : bs / a.strips;
+            strip = bs - b * a.strips;
             slot = g - cta_of_unit(bs * a.ups, a.q, a.r);
             const float* p1b = a.p1 + (size_t)b * a.N * 3;
             const int row0 = strip * (kSweepThreads * R) + tid * R;
@@ -238,48 +280,106 @@ __global__ void __launch_bounds__(kSweepThreads, (R >= 16 ? 4 : 6)) chamfer_swee
                 sPrev[k][tid] = CUDART_INF_F;
                 sSubIdx[k][tid] = cbeg / kSub;
             }
+            if (PACKED) {
+#pragma unroll
+                for (int k = 0; k < R / 2; ++k) {
+                    PX[k] = pack2(px[2 * k], px[2 * k + 1]);
+                    PY[k] = pack2(py[2 * k], py[2 * k + 1]);
+                    PZ[k] = pack2(pz[2 * k], pz[2 * k + 1]);
+                }
+            }
         }
         __syncwarp();  // tile visible to the whole warp
-        if (unext < uend) fetch(unext);  // overlaps the whole sub-block below
+        if (nleft > 0) fetch(nbs, ncu, piece_units(ncu, nleft));  // overlaps the whole sub-block below
 
         const int ncols = cend - cbeg;
         const int nsteps = (ncols + 3) >> 2;
         const float* tile = sCols[w];
         u64* res = sColRes[w];
+
+        if (!PACKED) {
 #pragma unroll 1
-        for (int step = 0; step < nsteps; ++step) {
-            const float4 v0 = *reinterpret_cast<const float4*>(tile + 12 * step);      // x0 y0 z0 x1
-            const float4 v1 = *reinterpret_cast<const float4*>(tile + 12 * step + 4);  // y1 z1 x2 y2
-            const float4 v2 = *reinterpret_cast<const float4*>(tile + 12 * step + 8);  // z2 x3 y3 z3
-            float c0m = CUDART_INF_F, c1m = CUDART_INF_F, c2m = CUDART_INF_F, c3m = CUDART_INF_F;
+            for (int step = 0; step < nsteps; ++step) {
+                const float4 v0 = *reinterpret_cast<const float4*>(tile + 12 * step);      // x0 y0 z0 x1
+                const float4 v1 = *reinterpret_cast<const float4*>(tile + 12 * step + 4);  // y1 z1 x2 y2
+                const float4 v2 = *reinterpret_cast<const float4*>(tile + 12 * step + 8);  // z2 x3 y3 z3
+                float c0m = CUDART_INF_F, c1m = CUDART_INF_F, c2m = CUDART_INF_F, c3m = CUDART_INF_F;
 #pragma unroll
-            for (int k = 0; k < R; k += 2) {
-                const float a0 = sqdist(px[k], py[k], pz[k], v0.x, v0.y, v0.z);
-                const float a1 = sqdist(px[k], py[k], pz[k], v0.w, v1.x, v1.y);
-                const float a2 = sqdist(px[k], py[k], pz[k], v1.z, v1.w, v2.x);
-                const float a3 = sqdist(px[k], py[k], pz[k], v2.y, v2.z, v2.w);
-                const float b0 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v0.x, v0.y, v0.z);
-                const float b1 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v0.w, v1.x, v1.y);
-                const float b2 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v1.z, v1.w, v2.x);
-                const float b3 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v2.y, v2.z, v2.w);
-                best[k] = min3(min3(best[k], a0, a1), a2, a3);
-                best[k + 1] = min3(min3(best[k + 1], b0, b1), b2, b3);
-                c0m = min3(c0m, a0, b0);
-                c1m = min3(c1m, a1, b1);
-                c2m = min3(c2m, a2, b2);
-                c3m = min3(c3m, a3, b3);
+                for (int k = 0; k < R; k += 2) {
+                    const float a0 = sqdist(px[k], py[k], pz[k], v0.x, v0.y, v0.z);
+                    const float a1 = sqdist(px[k], py[k], pz[k], v0.w, v1.x, v1.y);
+                    const float a2 = sqdist(px[k], py[k], pz[k], v1.z, v1.w, v2.x);
+                    const float a3 = sqdist(px[k], py[k], pz[k], v2.y, v2.z, v2.w);
+                    const float b0 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v0.x, v0.y, v0.z);
+                    const float b1 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v0.w, v1.x, v1.y);
+                    const float b2 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v1.z, v1.w, v2.x);
+                    const float b3 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v2.y, v2.z, v2.w);
+                    best[k] = min3(min3(best[k], a0, a1), a2, a3);
+                    best[k + 1] = min3(min3(best[k + 1], b0, b1), b2, b3);
+                    c0m = min3(c0m, a0, b0);
+                    c1m = min3(c1m, a1, b1);
+                    c2m = min3(c2m, a2, b2);
+                    c3m = min3(c3m, a3, b3);
+                }
+                // column direction: warp minimum + the lanes that attain it, one 8-byte record per column
+                const float m0 = warp_min_f32(c0m), m1 = warp_min_f32(c1m), m2 = warp_min_f32(c2m), m3 = warp_min_f32(c3m);
+                const unsigned h0 = __ballot_sync(0xffffffffu, c0m == m0);
+                const unsigned h1 = __ballot_sync(0xffffffffu, c1m == m1);
+                const unsigned h2 = __ballot_sync(0xffffffffu, c2m == m2);
+                const unsigned h3 = __ballot_sync(0xffffffffu, c3m == m3);
+                if (lane == 0) {
+                    res[4 * step + 0] = ((u64)__float_as_uint(m0) << 32) | h0;
+                    res[4 * step + 1] = ((u64)__float_as_uint(m1) << 32) | h1;
+                    res[4 * step + 2] = ((u64)__float_as_uint(m2) << 32) | h2;
+                    res[4 * step + 3] = ((u64)__float_as_uint(m3) << 32) | h3;
+                }
             }
-            // column direction: warp minimum + the lanes that attain it, one 8-byte record per column
-            const float m0 = warp_min_f32(c0m), m1 = warp_min_f32(c1m), m2 = warp_min_f32(c2m), m3 = warp_min_f32(c3m);
-            const unsigned h0 = __ballot_sync(0xffffffffu, c0m == m0);
-            const unsigned h1 = __ballot_sync(0xffffffffu, c1m == m1);
-            const unsigned h2 = __ballot_sync(0xffffffffu, c2m == m2);
-            const unsigned h3 = __ballot_sync(0xffffffffu, c3m == m3);
-            if (lane == 0) {
-                res[4 * step + 0] = ((u64)__float_as_uint(m0) << 32) | h0;
-                res[4 * step + 1] = ((u64)__float_as_uint(m1) << 32) | h1;
-                res[4 * step + 2] = ((u64)__float_as_uint(m2) << 32) | h2;
-                res[4 * step + 3] = ((u64)__float_as_uint(m3) << 32) | h3;
+        } else {
+            const ulonglong2* txy = reinterpret_cast<const ulonglong2*>(tile);           // [c] = ((x,x), (y,y))
+            const ulonglong2* tz = reinterpret_cast<const ulonglong2*>(tile + 4 * kSub);  // [c/2] = ((z,z), (z',z'))
+#pragma unroll 1
+            for (int step = 0; step < nsteps; ++step) {
+                u64 QX[4], QY[4], QZ[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const ulonglong2 xy = txy[4 * step + c];
+                    QX[c] = xy.x;
+                    QY[c] = xy.y;
+                }
+                {
+                    const ulonglong2 z01 = tz[2 * step], z23 = tz[2 * step + 1];
+                    QZ[0] = z01.x;
+                    QZ[1] = z01.y;
+                    QZ[2] = z23.x;
+                    QZ[3] = z23.y;
+                }
+                float cm[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
+#pragma unroll
+                for (int k = 0; k < R / 2; ++k) {
+                    float lo[4], hi[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const u64 dx = sub2(QX[c], PX[k]), dy = sub2(QY[c], PY[k]), dz = sub2(QZ[c], PZ[k]);
+                        u64 t = mul2(dy, dy);
+                        t = fma2(dx, dx, t);
+                        t = fma2(dz, dz, t);
+                        unpack2(t, lo[c], hi[c]);
+                        cm[c] = min3(cm[c], lo[c], hi[c]);
+                    }
+                    best[2 * k] = min3(min3(best[2 * k], lo[0], lo[1]), lo[2], lo[3]);
+                    best[2 * k + 1] = min3(min3(best[2 * k + 1], hi[0], hi[1]), hi[2], hi[3]);
+                }
+                const float m0 = warp_min_f32(cm[0]), m1 = warp_min_f32(cm[1]), m2 = warp_min_f32(cm[2]), m3 = warp_min_f32(cm[3]);
+                const unsigned h0 = __ballot_sync(0xffffffffu, cm[0] == m0);
+                const unsigned h1 = __ballot_sync(0xffffffffu, cm[1] == m1);
+                const unsigned h2 = __ballot_sync(0xffffffffu, cm[2] == m2);
+                const unsigned h3 = __ballot_sync(0xffffffffu, cm[3] == m3);
+                if (lane == 0) {
+                    res[4 * step + 0] = ((u64)__float_as_uint(m0) << 32) | h0;
+                    res[4 * step + 1] = ((u64)__float_as_uint(m1) << 32) | h1;
+                    res[4 * step + 2] = ((u64)__float_as_uint(m2) << 32) | h2;
+                    res[4 * step + 3] = ((u64)__float_as_uint(m3) << 32) | h3;
+                }
             }
         }
 
@@ -302,18 +402,16 @@ __global__ void __launch_bounds__(kSweepThreads, (R >= 16 ? 4 : 6)) chamfer_swee
         }
 
         // last piece of this (pair, strip) for this CTA: flush the row partials
-        {
-            int nbs = -1;
-            if (unext < uend) nbs = unext / a.ups;
-            if (nbs != bs) {
-                ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.rowpart + ((size_t)bs * a.maxslots + slot) * (kSweepThreads * R) + tid * R);
+        if (nleft == 0 || nbs != bs) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.rowpart + ((size_t)bs * a.maxslots + slot) * (kSweepThreads * R) + tid * R);
 #pragma unroll
-                for (int k = 0; k < R; k += 2)
-                    dst[k >> 1] = make_ulonglong2(((u64)__float_as_uint(best[k]) << 32) | (unsigned)sSubIdx[k][tid],
-                                                  ((u64)__float_as_uint(best[k + 1]) << 32) | (unsigned)sSubIdx[k + 1][tid]);
-            }
+            for (int k = 0; k < R; k += 2)
+                dst[k >> 1] = make_ulonglong2(((u64)__float_as_uint(best[k]) << 32) | (unsigned)sSubIdx[k][tid],
+                                              ((u64)__float_as_uint(best[k + 1]) << 32) | (unsigned)sSubIdx[k + 1][tid]);
         }
-        u = unext;
+        bs = nbs;
+        cu = ncu;
+        left = nleft;
     }
 }
 
@@ -550,18 +648,15 @@ int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M
     unsigned* counters = loss ? reinterpret_cast<unsigned*>(base + pl.counters_off) : nullptr;
 
     const SweepArgs sa{p1, p2, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart, counters, B};
-    switch (pl.R) {
-        case 16:
-            chamfer_sweep_kernel<16><<<pl.grid, kSweepThreads, 0, stream>>>(sa);
-            break;
-        case 8:
-            chamfer_sweep_kernel<8><<<pl.grid, kSweepThreads, 0, stream>>>(sa);
-            break;
-        default:
-            chamfer_sweep_kernel<4><<<pl.grid, kSweepThreads, 0, stream>>>(sa);
-            break;
-    }
-    FPSG_CUDA_OK(cudaGetLastError());
+    const dim3 sgrid((unsigned)pl.grid), sblock(kSweepThreads);
+    if (pl.R == 16 && pl.packed)
+        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<16, true>, sgrid, sblock, 0, stream, sa));
+    else if (pl.R == 16)
+        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<16, false>, sgrid, sblock, 0, stream, sa));
+    else if (pl.R == 8)
+        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<8, false>, sgrid, sblock, 0, stream, sa));
+    else
+        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<4, false>, sgrid, sblock, 0, stream, sa));
     if (sweep_only) return FPSG_OK;
     const FinalizeArgs fa{p1, p2, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart,
                           dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb, getenv("FPSG_FIN_DBG") ? atoi(getenv("FPSG_FIN_DBG")) : 0};
