@@ -40,8 +40,8 @@ B_PER_GPU, N_PTS, M_PTS = 32, 2048, 2048
 WORKLOAD = "c1: Chamfer loss fwd+bwd(p1), B=32 per GPU, N=M=2048, synthetic xyz float32"
 METRIC = "chamfer_fwd_bwd_pairs_per_s"
 RING_SETS = 96  # distinct input batches cycled through: 96 x 1.57 MB = 151 MB > 126 MB L2
-# dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch, from profiles/r01_sweep_ncu_summary.md
-SWEEP_DRAM_TRAFFIC_BYTES = 1.59e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch (profiles/r01_chamfer_kernels_raw.csv, r01_summary.md)
+SWEEP_DRAM_TRAFFIC_BYTES = 1.597e6
 
 
 def make_inputs(batch, n, m, seed, device=None, pin=False):
@@ -74,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -182,7 +182,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
     args = ap.parse_args()
@@ -230,7 +230,8 @@ def main():
     loss = torch.empty(B, device=dev)
     gloss = torch.ones(B, device=dev)
     gp1 = torch.empty(B, N, 3, device=dev)
-    total = torch.zeros((), device=dev)
+    totals = [torch.zeros((), device=dev), torch.zeros((), device=dev)]
+    pending = [None, None]
     nbytes = L.fpsg_chamfer_fwd_workspace_bytes(B, N, M)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
@@ -242,11 +243,15 @@ def main():
         a, b = ptrs[i % RING_SETS]
         _lib.check(L.fpsg_chamfer_loss_fwd(a, b, B, N, M, 1.0, 1.0, o[0], o[1], o[2], o[3], o[4], o[5], nbytes, sp))
         if world > 1:
-            torch.sum(loss, out=total)
-            work = dist.all_reduce(total, op=dist.ReduceOp.SUM, async_op=True)
+            # the scalar the reference logs: all-reduced asynchronously, consumed one step later, so the
+            # collective's latency overlaps the backward and the next forward instead of stalling the stream
+            k = i & 1
+            torch.sum(loss, dim=0, out=totals[k])
+            pending[k] = dist.all_reduce(totals[k], op=dist.ReduceOp.SUM, async_op=True)
         _lib.check(L.fpsg_chamfer_loss_bwd(a, b, o[3], o[4], o[6], 1.0, 1.0, B, N, M, o[7], None, None, 0, sp))
-        if world > 1:
-            work.wait()
+        if world > 1 and pending[(i + 1) & 1] is not None:
+            pending[(i + 1) & 1].wait()
+            pending[(i + 1) & 1] = None
 
     kernels_per_step = 4  # sweep, finalize, loss, backward (the NCCL kernel for N > 1 is not ours)
 
@@ -255,18 +260,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~0.1 s to deliver its first sample: start it ahead of the warm-up
     for i in range(args.warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
     for i in range(args.steps):
-        step(args.warmup + i)
+        step(args.warmup + i)  # same parity/ring phase as the warm-up left it
     e1.record(stream)
+    for k in (0, 1):
+        if pending[k] is not None:
+            pending[k].wait()
+            pending[k] = None
     barrier()
     ms = e0.elapsed_time(e1)
 
@@ -364,7 +373,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "api": "kaolin.metrics.pointcloud.chamfer_distance(p1, p2).sum().backward() (fpsg_b200 shim), pinned host inputs"},
             "gpu_launches": kernels_per_step * args.steps,
-            "roofline": {"bound": "fp32_fma", "kernel": "chamfer_sweep_kernel<16>", "achieved": achieved, "peak": fp32_peak_tflops,
+            "roofline": {"bound": "fp32_fma", "kernel": "chamfer_sweep_kernel<16,false>", "achieved": achieved, "peak": fp32_peak_tflops,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": SWEEP_DRAM_TRAFFIC_BYTES,
                          "us_per_launch": sweep_us, "algorithmic_flop_per_launch": flops,
                          "peak_source": f"FFMA micro-kernel in this run (fpsg_probe_fp32_peak) at {probe_mhz:.0f} MHz; MEASURED_PEAKS.json has no FP32 row; "
