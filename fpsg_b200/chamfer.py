@@ -41,8 +41,34 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def _workspace(nbytes: int, device) -> torch.Tensor:
-    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+class _device_guard:
+    """torch.cuda.device(dev) only when dev is not already current (the common case costs nothing)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+_WS_BYTES = {}  # (B, N, M) -> workspace size; the query is pure arithmetic, cache it
+
+
+def _workspace(B: int, N: int, M: int, device) -> tuple[torch.Tensor, int]:
+    key = (B, N, M, device.index)
+    nbytes = _WS_BYTES.get(key)
+    if nbytes is None:
+        nbytes = int(_lib.lib().fpsg_chamfer_fwd_workspace_bytes(B, N, M))
+        _WS_BYTES[key] = nbytes
+    # a fresh caching-allocator block per call: safe under multi-stream use, and the allocator makes it cheap
+    return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device), nbytes
 
 
 def _forward(p1: torch.Tensor, p2: torch.Tensor, want_loss: bool, w1: float = 1.0, w2: float = 1.0):
@@ -51,19 +77,23 @@ def _forward(p1: torch.Tensor, p2: torch.Tensor, want_loss: bool, w1: float = 1.
     B, N, _ = p1.shape
     M = p2.shape[1]
     dev = p1.device
-    dist1 = torch.empty((B, N), dtype=torch.float32, device=dev)
-    dist2 = torch.empty((B, M), dtype=torch.float32, device=dev)
-    idx1 = torch.empty((B, N), dtype=torch.int64, device=dev)
-    idx2 = torch.empty((B, M), dtype=torch.int64, device=dev)
-    loss = torch.empty((B,), dtype=torch.float32, device=dev) if want_loss else None
+    idx = torch.empty((B * (N + M),), dtype=torch.int64, device=dev)  # one allocation for both index outputs
+    idx1 = idx[:B * N].view(B, N)
+    idx2 = idx[B * N:].view(B, M)
+    if want_loss:  # the fused loss path needs no per-point distances
+        dist1 = dist2 = None
+        loss = torch.empty((B,), dtype=torch.float32, device=dev)
+    else:
+        dist1 = torch.empty((B, N), dtype=torch.float32, device=dev)
+        dist2 = torch.empty((B, M), dtype=torch.float32, device=dev)
+        loss = None
     if B == 0:
         return dist1, dist2, idx1, idx2, loss
-    with torch.cuda.device(dev):
-        nbytes = L.fpsg_chamfer_fwd_workspace_bytes(B, N, M)
-        ws = _workspace(nbytes, dev)
+    with _device_guard(dev):
+        ws, nbytes = _workspace(B, N, M, dev)
         if want_loss:
             rc = L.fpsg_chamfer_loss_fwd(p1.data_ptr(), p2.data_ptr(), B, N, M, float(w1), float(w2), loss.data_ptr(),
-                                         dist1.data_ptr(), dist2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
+                                         None, None, idx1.data_ptr(), idx2.data_ptr(),
                                          ws.data_ptr(), nbytes, _stream_ptr(dev))
         else:
             rc = L.fpsg_chamfer_fwd(p1.data_ptr(), p2.data_ptr(), B, N, M, dist1.data_ptr(), dist2.data_ptr(),
@@ -83,7 +113,7 @@ def _backward(p1, p2, idx1, idx2, g1, g2, need1: bool, need2: bool):
         return gp1, gp2
     g1 = g1.to(torch.float32).contiguous()
     g2 = g2.to(torch.float32).contiguous()
-    with torch.cuda.device(dev):
+    with _device_guard(dev):
         rc = L.fpsg_chamfer_bwd(p1.data_ptr(), p2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), g1.data_ptr(),
                                 g2.data_ptr(), B, N, M, gp1.data_ptr() if need1 else None,
                                 gp2.data_ptr() if need2 else None, None, 0, _stream_ptr(dev))
@@ -145,7 +175,7 @@ class _ChamferLoss(torch.autograd.Function):
         gp2 = torch.empty_like(p2) if need2 else None
         if B > 0 and (need1 or need2):
             gloss = gloss.to(torch.float32).contiguous()
-            with torch.cuda.device(dev):
+            with _device_guard(dev):
                 rc = L.fpsg_chamfer_loss_bwd(p1.data_ptr(), p2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
                                              gloss.data_ptr(), ctx.w[0], ctx.w[1], B, N, M,
                                              gp1.data_ptr() if need1 else None, gp2.data_ptr() if need2 else None,

@@ -13,6 +13,8 @@
 //   pd   = rn( rn(-xx_j + 2*dot) - xx_i )               (model.py:16; -2*dot is exact, so the first
 //                                                        subtraction is one rounding = fma(2, dot, -xx_j))
 // Ranking: larger pd first; equal pd ordered by ascending index (torch.topk leaves ties unspecified).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fpsg {
@@ -37,6 +39,27 @@ __global__ void __launch_bounds__(256) knn_sqnorm_kernel(const float* __restrict
     xx[(size_t)b * N + j] = s;
 }
 
+// Asynchronous global->shared copy of one float (LDGSTS): a whole tile is issued without waiting for any element,
+// so a tile load costs one memory latency instead of one per row of the tile.
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// loads the [C][jn] block x[:, j0:j0+jn] and the matching squared norms into shared memory (row stride J)
+__device__ __forceinline__ void knn_load_tile(float* sTile, float* sXX, const float* __restrict__ xb, const float* __restrict__ xxb,
+                                              int C, int N, int J, int j0, int jn, int tid) {
+    const int chunks = (jn + 31) >> 5;  // 32-column chunks per channel row
+    const int lane = tid & 31, w = tid >> 5;
+    for (int item = w; item < C * chunks; item += kKnnWarps) {
+        const int c = item / chunks, jj = (item - c * chunks) * 32 + lane;
+        if (jj < jn) cp_async_f32(sTile + (size_t)c * J + jj, xb + (size_t)c * N + j0 + jj);
+    }
+    for (int jj = tid; jj < jn; jj += kKnnThreads) cp_async_f32(sXX + jj, xxb + j0 + jj);
+    cp_async_wait_all();
+}
+
 // KR = list registers per lane (k <= 32*KR); C3 = channel count is exactly 3 (query point kept in registers)
 template <int KR, bool C3>
 __global__ void __launch_bounds__(kKnnThreads)
@@ -58,9 +81,7 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int
     for (int j0 = 0; j0 < N; j0 += J) {
         const int jn = min(J, N - j0);
         __syncthreads();  // previous tile fully consumed
-        for (int c = 0; c < C; ++c)
-            for (int jj = tid; jj < jn; jj += kKnnThreads) sTile[(size_t)c * J + jj] = __ldg(xb + (size_t)c * N + j0 + jj);
-        for (int jj = tid; jj < jn; jj += kKnnThreads) sXX[jj] = __ldg(xxb + j0 + jj);
+        knn_load_tile(sTile, sXX, xb, xxb, C, N, J, j0, jn, tid);
         __syncthreads();
 
         for (int rr = 0; rr < kKnnRowsPerWarp; ++rr) {
@@ -166,6 +187,298 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int
     }
 }
 
+// Generic channel count: every warp owns QB query points for the whole kernel (their top-k lists never leave
+// registers) and scores 32 candidates per step against all QB of them: per channel one candidate value per lane
+// (LDS), the QB query values by broadcast (LDS.128) and QB FFMAs -- a register-blocked FP32 inner product. The
+// candidate tiles ([C][J] floats) are shared by the CTA's warps.
+constexpr int kKnnQB = 8;
+
+template <int KR>
+__global__ void __launch_bounds__(kKnnThreads)
+knn_blocked_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int k, int J, int64_t* __restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sTile = reinterpret_cast<float*>(smem_raw);  // [C][J]
+    float* sXX = sTile + (size_t)C * J;                 // [J]
+    float* sQ = sXX + J;                                // [kKnnWarps][C][kKnnQB] query values, channel-major
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int b = blockIdx.y;
+    const int i0 = (blockIdx.x * kKnnWarps + w) * kKnnQB;  // first query point of this warp
+    const float* __restrict__ xb = x + (size_t)b * C * N;
+    const float* __restrict__ xxb = xx + (size_t)b * N;
+    const int kth_lane = (k - 1) & 31, kth_reg = (k - 1) >> 5;
+    float* myQ = sQ + (size_t)w * C * kKnnQB;
+
+    // query values and norms (rows past N are clamped: they compute garbage that is never written)
+    for (int e = lane; e < C * kKnnQB; e += 32) {
+        const int c = e / kKnnQB, q = e - c * kKnnQB;
+        myQ[e] = __ldg(xb + (size_t)c * N + min(i0 + q, N - 1));
+    }
+    float xxi[kKnnQB], tau[kKnnQB];
+    float lv[kKnnQB][KR];
+    int li[kKnnQB][KR];
+#pragma unroll
+    for (int q = 0; q < kKnnQB; ++q) {
+        xxi[q] = __ldg(xxb + min(i0 + q, N - 1));
+        tau[q] = -CUDART_INF_F;
+#pragma unroll
+        for (int r = 0; r < KR; ++r) {
+            lv[q][r] = -CUDART_INF_F;
+            li[q][r] = 0;
+        }
+    }
+    __syncwarp();
+
+    for (int j0 = 0; j0 < N; j0 += J) {
+        const int jn = min(J, N - j0);
+        __syncthreads();  // previous tile fully consumed
+        knn_load_tile(sTile, sXX, xb, xxb, C, N, J, j0, jn, tid);
+        __syncthreads();
+        if (i0 >= N) continue;  // warp-uniform; the warp still takes part in the barriers
+
+        for (int jb = 0; jb < jn; jb += 32) {
+            const int jj = min(jb + lane, jn - 1);  // clamped lanes are masked out below
+            float dot[kKnnQB];
+#pragma unroll
+            for (int q = 0; q < kKnnQB; ++q) dot[q] = 0.f;
+#pragma unroll 4
+            for (int c = 0; c < C; ++c) {
+                const float cv = sTile[(size_t)c * J + jj];
+                const float4 qa = *reinterpret_cast<const float4*>(myQ + c * kKnnQB);
+                const float4 qb = *reinterpret_cast<const float4*>(myQ + c * kKnnQB + 4);
+                dot[0] = __fmaf_rn(qa.x, cv, dot[0]);
+                dot[1] = __fmaf_rn(qa.y, cv, dot[1]);
+                dot[2] = __fmaf_rn(qa.z, cv, dot[2]);
+                dot[3] = __fmaf_rn(qa.w, cv, dot[3]);
+                dot[4] = __fmaf_rn(qb.x, cv, dot[4]);
+                dot[5] = __fmaf_rn(qb.y, cv, dot[5]);
+                dot[6] = __fmaf_rn(qb.z, cv, dot[6]);
+                dot[7] = __fmaf_rn(qb.w, cv, dot[7]);
+            }
+            const float nxx = -sXX[jj];
+            const bool inb = jb + lane < jn;
+#pragma unroll
+            for (int q = 0; q < kKnnQB; ++q) {
+                const float pd = inb ? __fsub_rn(__fmaf_rn(2.0f, dot[q], nxx), xxi[q]) : -CUDART_INF_F;
+                unsigned mask = __ballot_sync(0xffffffffu, pd > tau[q]);
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float v = __shfl_sync(0xffffffffu, pd, src);
+                    if (!(v > tau[q])) continue;  // tau rose since the ballot
+                    const int vj = j0 + jb + src;
+                    int pos = 0;
+#pragma unroll
+                    for (int r = 0; r < KR; ++r) pos += __popc(__ballot_sync(0xffffffffu, lv[q][r] >= v));
+#pragma unroll
+                    for (int r = KR - 1; r >= 0; --r) {
+                        float pv = __shfl_up_sync(0xffffffffu, lv[q][r], 1);
+                        int pi = __shfl_up_sync(0xffffffffu, li[q][r], 1);
+                        if (r > 0) {
+                            const float cv2 = __shfl_sync(0xffffffffu, lv[q][r - 1], 31);
+                            const int ci = __shfl_sync(0xffffffffu, li[q][r - 1], 31);
+                            if (lane == 0) {
+                                pv = cv2;
+                                pi = ci;
+                            }
+                        }
+                        const int e = r * 32 + lane;
+                        if (e > pos) {
+                            lv[q][r] = pv;
+                            li[q][r] = pi;
+                        } else if (e == pos) {
+                            lv[q][r] = v;
+                            li[q][r] = vj;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < KR; ++r)
+                        if (r == kth_reg) tau[q] = __shfl_sync(0xffffffffu, lv[q][r], kth_lane);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kKnnQB; ++q) {
+        if (i0 + q < N) {
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                const int e = r * 32 + lane;
+                if (e < k) idx[((size_t)b * N + i0 + q) * k + e] = li[q][r];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k <= 32: bulk top-k. The sorted list of a query is one 64-bit key per lane,
+//   key = (order-preserving bits of pd) << 32 | (0xFFFFFFFF - j)      larger key = better, lower j wins ties,
+// and candidates that beat the current k-th value are not inserted one by one but parked in a 64-slot
+// shared-memory buffer (ballot + rank). Only when 32 have piled up -- about five times per query at N = 1024,
+// because every flush raises the threshold -- are they sorted by a warp bitonic network and merged into the list
+// (reverse, element-wise max, bitonic merge). Cost per buffered candidate ~5 instructions instead of ~35 for a
+// shuffle insertion.
+// ---------------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+
+__device__ __forceinline__ unsigned f32_to_ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return u ^ (((int)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_f32(unsigned o) {
+    return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+__device__ __forceinline__ u64 key_cmpx(u64 key, int d, bool take_max) {
+    const u64 o = __shfl_xor_sync(0xffffffffu, key, d);
+    const bool gt = key > o;
+    return (gt == take_max) ? key : o;
+}
+// sorts the warp's 32 keys descending by lane
+__device__ __forceinline__ u64 warp_sort_desc(u64 key, int lane) {
+#pragma unroll
+    for (int s = 2; s <= 32; s <<= 1) {
+        const bool desc = s == 32 ? true : ((lane & s) == 0);
+#pragma unroll
+        for (int d = s >> 1; d > 0; d >>= 1) key = key_cmpx(key, d, ((lane & d) == 0) == desc);
+    }
+    return key;
+}
+// bitonic sequence -> descending
+__device__ __forceinline__ u64 warp_merge_desc(u64 key, int lane) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) key = key_cmpx(key, d, (lane & d) == 0);
+    return key;
+}
+
+// Sorts up to 64 buffered candidate keys and merges them into the sorted list `key` (one entry per lane). Kept out
+// of line on purpose: eight inlined copies (one per query of the warp) overflow the instruction cache.
+__device__ __noinline__ u64 knn_flush_list(u64 key, const u64* buf, int cnt) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        if (cnt > 32 * h) {  // warp-uniform
+            u64 kb = 32 * h + lane < cnt ? buf[32 * h + lane] : 0ull;
+            kb = warp_sort_desc(kb, lane);
+            const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
+            key = warp_merge_desc(key > rev ? key : rev, lane);
+        }
+    }
+    __syncwarp();
+    return key;
+}
+
+template <bool C3>
+__global__ void __launch_bounds__(kKnnThreads)
+knn_bulk_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int k, int J, int64_t* __restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sTile = reinterpret_cast<float*>(smem_raw);  // [C][J]
+    float* sXX = sTile + (size_t)C * J;                 // [J]
+    float* sQ = sXX + J;                                // [kKnnWarps][C][kKnnQB] query values (generic C only)
+    u64* sBuf = reinterpret_cast<u64*>(sQ + (C3 ? 0 : (size_t)kKnnWarps * C * kKnnQB));  // [kKnnWarps][kKnnQB][64]
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int b = blockIdx.y;
+    const int i0 = (blockIdx.x * kKnnWarps + w) * kKnnQB;  // first query point of this warp
+    const float* __restrict__ xb = x + (size_t)b * C * N;
+    const float* __restrict__ xxb = xx + (size_t)b * N;
+    float* myQ = sQ + (size_t)w * C * kKnnQB;
+    u64* myBuf = sBuf + (size_t)w * kKnnQB * 64;
+
+    float q0[kKnnQB], q1[kKnnQB], q2[kKnnQB];  // C3: the query points themselves
+    float xxi[kKnnQB], tau[kKnnQB];
+    u64 key[kKnnQB];
+    int cnt[kKnnQB];
+#pragma unroll
+    for (int q = 0; q < kKnnQB; ++q) {
+        const int i = min(i0 + q, N - 1);  // rows past N are clamped: computed, never written
+        if (C3) {
+            q0[q] = __ldg(xb + i);
+            q1[q] = __ldg(xb + (size_t)N + i);
+            q2[q] = __ldg(xb + 2 * (size_t)N + i);
+        }
+        xxi[q] = __ldg(xxb + i);
+        tau[q] = -CUDART_INF_F;
+        key[q] = 0ull;
+        cnt[q] = 0;
+    }
+    if (!C3) {
+        for (int e = lane; e < C * kKnnQB; e += 32) {
+            const int c = e / kKnnQB, q = e - c * kKnnQB;
+            myQ[e] = __ldg(xb + (size_t)c * N + min(i0 + q, N - 1));
+        }
+        __syncwarp();
+    }
+
+    // sorts the buffered candidates of query q and merges them into its list; refreshes the threshold
+    auto flush = [&](int q) {
+        key[q] = knn_flush_list(key[q], myBuf + q * 64, cnt[q]);
+        cnt[q] = 0;
+        const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(key[q] >> 32), k - 1);
+        tau[q] = hi ? ord_to_f32(hi) : -CUDART_INF_F;  // fewer than k entries so far: everything passes
+    };
+
+    for (int j0 = 0; j0 < N; j0 += J) {
+        const int jn = min(J, N - j0);
+        __syncthreads();  // previous tile fully consumed
+        knn_load_tile(sTile, sXX, xb, xxb, C, N, J, j0, jn, tid);
+        __syncthreads();
+        if (i0 >= N) continue;  // warp-uniform; the warp still takes part in the barriers
+
+        for (int jb = 0; jb < jn; jb += 32) {
+            const int jj = min(jb + lane, jn - 1);  // clamped lanes are masked out below
+            const bool inb = jb + lane < jn;
+            float dot[kKnnQB];
+            if (C3) {
+                const float c0 = sTile[jj], c1 = sTile[J + jj], c2 = sTile[2 * J + jj];
+#pragma unroll
+                for (int q = 0; q < kKnnQB; ++q) {
+                    float d = __fmul_rn(q0[q], c0);
+                    d = __fmaf_rn(q1[q], c1, d);
+                    dot[q] = __fmaf_rn(q2[q], c2, d);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < kKnnQB; ++q) dot[q] = 0.f;
+#pragma unroll 4
+                for (int c = 0; c < C; ++c) {
+                    const float cv = sTile[(size_t)c * J + jj];
+                    const float4 qa = *reinterpret_cast<const float4*>(myQ + c * kKnnQB);
+                    const float4 qb = *reinterpret_cast<const float4*>(myQ + c * kKnnQB + 4);
+                    dot[0] = __fmaf_rn(qa.x, cv, dot[0]);
+                    dot[1] = __fmaf_rn(qa.y, cv, dot[1]);
+                    dot[2] = __fmaf_rn(qa.z, cv, dot[2]);
+                    dot[3] = __fmaf_rn(qa.w, cv, dot[3]);
+                    dot[4] = __fmaf_rn(qb.x, cv, dot[4]);
+                    dot[5] = __fmaf_rn(qb.y, cv, dot[5]);
+                    dot[6] = __fmaf_rn(qb.z, cv, dot[6]);
+                    dot[7] = __fmaf_rn(qb.w, cv, dot[7]);
+                }
+            }
+            const float nxx = -sXX[jj];
+            const unsigned jkey = 0xffffffffu - (unsigned)(j0 + jb + lane);
+#pragma unroll
+            for (int q = 0; q < kKnnQB; ++q) {
+                const float pd = __fsub_rn(__fmaf_rn(2.0f, dot[q], nxx), xxi[q]);
+                const bool pass = inb && pd > tau[q];
+                const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                if (mask) {  // warp-uniform
+                    if (pass) myBuf[q * 64 + cnt[q] + __popc(mask & lt_mask)] = ((u64)f32_to_ord(pd) << 32) | jkey;
+                    cnt[q] += __popc(mask);
+                    if (cnt[q] >= 32) flush(q);
+                }
+            }
+        }
+    }
+    if (i0 >= N) return;
+#pragma unroll
+    for (int q = 0; q < kKnnQB; ++q) {
+        if (cnt[q] > 0) flush(q);
+        if (i0 + q < N && lane < k) idx[((size_t)b * N + i0 + q) * k + lane] = (int64_t)(0xffffffffu - (unsigned)key[q]);
+    }
+}
+
 struct KnnPlan {
     int KR;
     int J;
@@ -182,7 +495,12 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
     const int npad = (N + 31) / 32 * 32;
     if (j > npad) j = npad;
     p.J = (int)j;
-    p.smem = ((size_t)C * p.J + p.J + (C == 3 ? 0 : (size_t)kKnnWarps * C)) * sizeof(float) + (size_t)kKnnRows * 32 * p.KR * (sizeof(float) + sizeof(int));
+    if (p.KR == 1 && !getenv("FPSG_KNN_INSERT"))  // bulk top-k kernel: tile + (generic C) query values + candidate buffers
+        p.smem = ((size_t)C * p.J + p.J + (C == 3 ? 0 : (size_t)kKnnWarps * C * kKnnQB)) * sizeof(float) + (size_t)kKnnWarps * kKnnQB * 64 * sizeof(u64);
+    else if (C == 3)
+        p.smem = ((size_t)C * p.J + p.J) * sizeof(float) + (size_t)kKnnRows * 32 * p.KR * (sizeof(float) + sizeof(int));
+    else
+        p.smem = ((size_t)C * p.J + p.J + (size_t)kKnnWarps * C * kKnnQB) * sizeof(float);
     p.ws_bytes = align_up((size_t)B * N * sizeof(float), 256);
     return p;
 }
@@ -190,6 +508,26 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
 size_t knn_workspace(int B, int C, int N, int k) {
     if (B <= 0 || C < 1 || N < 1 || k < 1) return 0;
     return make_knn_plan(B, C, N, k).ws_bytes;
+}
+
+template <bool C3>
+static int knn_launch_bulk(const float* x, const float* xx, int B, int C, int N, int k, const KnnPlan& p, int64_t* idx, cudaStream_t stream) {
+    auto kern = knn_bulk_kernel<C3>;
+    if (p.smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    const dim3 grid((unsigned)cdiv(N, kKnnWarps * kKnnQB), (unsigned)B);
+    kern<<<grid, kKnnThreads, p.smem, stream>>>(x, xx, C, N, k, p.J, idx);
+    FPSG_CUDA_OK(cudaGetLastError());
+    return FPSG_OK;
+}
+
+template <int KR>
+static int knn_launch_blocked(const float* x, const float* xx, int B, int C, int N, int k, const KnnPlan& p, int64_t* idx, cudaStream_t stream) {
+    auto kern = knn_blocked_kernel<KR>;
+    if (p.smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    const dim3 grid((unsigned)cdiv(N, kKnnWarps * kKnnQB), (unsigned)B);
+    kern<<<grid, kKnnThreads, p.smem, stream>>>(x, xx, C, N, k, p.J, idx);
+    FPSG_CUDA_OK(cudaGetLastError());
+    return FPSG_OK;
 }
 
 template <int KR, bool C3>
@@ -218,9 +556,11 @@ int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx,
     const bool c3 = (C == 3);
     switch (p.KR) {
         case 1:
-            return c3 ? knn_launch_t<1, true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_t<1, false>(x, xx, B, C, N, k, p, idx, stream);
+            if (getenv("FPSG_KNN_INSERT"))  // tuning override: the shuffle-insertion kernels also serve k <= 32
+                return c3 ? knn_launch_t<1, true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_blocked<1>(x, xx, B, C, N, k, p, idx, stream);
+            return c3 ? knn_launch_bulk<true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_bulk<false>(x, xx, B, C, N, k, p, idx, stream);
         case 2:
-            return c3 ? knn_launch_t<2, true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_t<2, false>(x, xx, B, C, N, k, p, idx, stream);
+            return c3 ? knn_launch_t<2, true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_blocked<2>(x, xx, B, C, N, k, p, idx, stream);
         default:
             return c3 ? knn_launch_t<4, true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_t<4, false>(x, xx, B, C, N, k, p, idx, stream);
     }
