@@ -1,0 +1,16 @@
+import sys, torch
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fpsg_b200
+from tests.helpers import make_pair, make_cloud_cn
+for (B, N, M) in [(1, 1, 1), (2, 1, 70), (2, 70, 1), (3, 31, 33), (2, 513, 129), (1, 2049, 2047), (5, 2048, 2048), (1, 4100, 300), (2, 300, 4100)]:
+    p1, p2 = make_pair(B, N, M, seed=N + M)
+    a = p1.cuda().requires_grad_(True); b = p2.cuda().requires_grad_(True)
+    d1, d2, i1, i2 = fpsg_b200.chamfer_distance(a, b)
+    (d1.sum() + d2.sum()).backward()
+    l = fpsg_b200.chamfer_loss(a, b, 0.5, 2.0); l.sum().backward()
+    d, i = fpsg_b200.sided_distance(a, b); d.sum().backward()
+for (B, C, N, k) in [(2, 3, 100, 20), (1, 3, 33, 33), (2, 3, 257, 64), (1, 3, 300, 128), (2, 64, 300, 20), (1, 128, 200, 20), (2, 5, 77, 7), (1, 3, 1500, 1), (1, 70, 100, 40)]:
+    x = make_cloud_cn(B, C, N, seed=C + N)
+    fpsg_b200.knn(x.cuda(), k)
+torch.cuda.synchronize()
+print("sanitizer workload done")

@@ -433,7 +433,6 @@ struct FinalizeArgs {
     float* loss;
     float w1, w2;
     int nrb, ncb;
-    int dbg;  // experiment switches (FPSG_FIN_DBG), 0 in production
 };
 
 __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const FinalizeArgs a) {
@@ -451,10 +450,6 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
     float mine = 0.f;  // this thread's distance, for the loss partial
     cudaTriggerProgrammaticLaunchCompletion();  // a following backward may start to launch
     cudaGridDependencySynchronize();            // the sweep's partials are complete and visible from here on
-    if (a.dbg) sFound[tid] = 0;
-    if (a.dbg & 16) return;
-    if ((a.dbg & 32) && blk < a.nrb) return;
-    if ((a.dbg & 64) && blk >= a.nrb) return;
 
     if (blk < a.nrb) {
         // ---- rows: each thread merges the partials of the CTAs that covered its row's strip ... ----
@@ -496,7 +491,7 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
         const int last = a.M - 1;
         constexpr int kBatch = 8;  // rows whose candidate loads are put in flight together (the loop is latency-bound)
         constexpr int kH = kSub / 32;
-        for (int rb = 0; rb < ((a.dbg & 1) ? 0 : 32); rb += kBatch) {
+        for (int rb = 0; rb < 32; rb += kBatch) {
             float cx[kBatch][kH], cy[kBatch][kH], cz[kBatch][kH];
 #pragma unroll
             for (int r = 0; r < kBatch; ++r) {
@@ -528,7 +523,7 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
             }
         }
         __syncwarp();
-        if (valid && !(a.dbg & 256)) {
+        if (valid) {
             if (a.dist1) a.dist1[(size_t)b * a.N + i] = m;
             a.idx1[(size_t)b * a.N + i] = sFound[tid];
         }
@@ -563,7 +558,7 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
         const unsigned gmask = ((1u << R) - 1u) << (grp * R);  // R <= 16
         const int last = a.N - 1;
         constexpr int kCB = 4;  // iterations whose candidate loads are in flight together (R is a multiple of 4)
-        for (int ib = 0; ib < ((a.dbg & 2) ? 0 : R); ib += kCB) {
+        for (int ib = 0; ib < R; ib += kCB) {
             float rx[kCB], ry[kCB], rz[kCB];
 #pragma unroll
             for (int t = 0; t < kCB; ++t) {
@@ -590,7 +585,7 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
         }
     }
 
-    if (a.losspart && !(a.dbg & 4)) {
+    if (a.losspart) {
         // fixed-order block sum in double (lanes by shuffle tree, warps ascending); the last CTA of the pair to
         // arrive adds the per-CTA sums in index order, so the result does not depend on arrival order
         double v = (double)mine;
@@ -659,9 +654,9 @@ int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M
         FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<4, false>, sgrid, sblock, 0, stream, sa));
     if (sweep_only) return FPSG_OK;
     const FinalizeArgs fa{p1, p2, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart,
-                          dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb, getenv("FPSG_FIN_DBG") ? atoi(getenv("FPSG_FIN_DBG")) : 0};
+                          dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb};
     const dim3 fgrid((unsigned)(pl.nrb + pl.ncb), (unsigned)B);
-    if (!(fa.dbg & 8)) FPSG_CUDA_OK(launch_pdl(chamfer_finalize_kernel, fgrid, dim3(kFinThreads), 0, stream, fa));
+    FPSG_CUDA_OK(launch_pdl(chamfer_finalize_kernel, fgrid, dim3(kFinThreads), 0, stream, fa));
     FPSG_CUDA_OK(cudaGetLastError());
     return FPSG_OK;
 }
