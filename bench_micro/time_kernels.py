@@ -42,3 +42,17 @@ for (B, C, N, k) in KN:
     s = torch.cuda.current_stream().cuda_stream
     f = lambda: _lib.check(L.fpsg_knn_fwd(x.data_ptr(), B, C, N, k, idx.data_ptr(), ws.data_ptr(), nb, s))
     print(json.dumps({"knn": [B, C, N, k], "us": round(time_fn(f, 20, 3), 2)}))
+
+import fpsg_b200
+for (B, C, N, k) in ([(32, 64, 1024, 20)] if "--c1" in sys.argv else [(32, 3, 1024, 20), (32, 64, 1024, 20), (32, 128, 1024, 20)]):
+    x = make_cloud_cn(B, C, N).cuda(); idx = fpsg_b200.knn(x, k)
+    out = torch.empty(B, 2 * C, N, k, device="cuda"); gx = torch.empty(B, C, N, device="cuda")
+    nb = L.fpsg_edge_feature_bwd_workspace_bytes(B, C, N, k); ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    f = lambda: _lib.check(L.fpsg_edge_feature_fwd(x.data_ptr(), idx.data_ptr(), B, C, N, k, out.data_ptr(), s))
+    g = lambda: _lib.check(L.fpsg_edge_feature_bwd(out.data_ptr(), idx.data_ptr(), B, C, N, k, gx.data_ptr(), ws.data_ptr(), nb, s))
+    tf, tb = time_fn(f, 20, 3), time_fn(g, 20, 3)
+    nbytes = 8.0 * C * N * k * B
+    from oracle.torch_formulation import get_graph_feature_torch
+    tt = time_fn(lambda: get_graph_feature_torch(x, k=k, idx=idx), 10, 2)
+    print(json.dumps({"edge_feature": [B, C, N, k], "fwd_us": round(tf, 1), "fwd_GBs": round(nbytes / tf / 1e3), "bwd_us": round(tb, 1), "bwd_GBs": round(nbytes / tb / 1e3), "torch_reference_ops_fwd_us": round(tt, 1)}))

@@ -44,6 +44,12 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_knn_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     L.fpsg_knn_fwd.restype = c_int
     L.fpsg_knn_fwd.argtypes = [vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]
+    L.fpsg_edge_feature_fwd.restype = c_int
+    L.fpsg_edge_feature_fwd.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp]
+    L.fpsg_edge_feature_bwd_workspace_bytes.restype = c_size_t
+    L.fpsg_edge_feature_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    L.fpsg_edge_feature_bwd.restype = c_int
+    L.fpsg_edge_feature_bwd.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]
     L.fpsg_chamfer_sweep_only.restype = c_int
     L.fpsg_chamfer_sweep_only.argtypes = [vp, vp, c_int, c_int, c_int, vp, c_size_t, vp]
     L.fpsg_probe_fp32_peak.restype = c_int

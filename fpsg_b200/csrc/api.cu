@@ -24,6 +24,10 @@ int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M
 int chamfer_backward_launch(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2, const float* g1,
                             const float* g2, bool uniform, float w1, float w2, int B, int N, int M, float* gp1, float* gp2,
                             cudaStream_t stream);
+int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out, cudaStream_t stream);
+size_t edge_feature_backward_workspace(int B, int C, int N, int k);
+int edge_feature_backward_launch(const float* g, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws, size_t ws_bytes,
+                                 cudaStream_t stream);
 size_t knn_workspace(int B, int C, int N, int k);
 int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t stream);
 
@@ -105,6 +109,17 @@ size_t fpsg_knn_workspace_bytes(int B, int C, int N, int k) { return knn_workspa
 
 int fpsg_knn_fwd(const float* x, int B, int C, int N, int k, int64_t* idx, void* ws, size_t ws_bytes, fpsg_stream_t stream) {
     return knn_forward_launch(x, B, C, N, k, idx, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int fpsg_edge_feature_fwd(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out, fpsg_stream_t stream) {
+    return edge_feature_forward_launch(x, idx, B, C, N, k, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t fpsg_edge_feature_bwd_workspace_bytes(int B, int C, int N, int k) { return edge_feature_backward_workspace(B, C, N, k); }
+
+int fpsg_edge_feature_bwd(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws, size_t ws_bytes,
+                          fpsg_stream_t stream) {
+    return edge_feature_backward_launch(gout, idx, B, C, N, k, gx, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int fpsg_probe_fp32_peak(double* tflops_host, double* sm_mhz_host, fpsg_stream_t stream_) {

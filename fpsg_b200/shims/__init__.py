@@ -35,14 +35,19 @@ def install(force: bool = False, patch_dgcnn: bool = True) -> None:
         patch_dgcnn_knn()
 
 
-def patch_dgcnn_knn(module=None) -> bool:
-    """Rebinds ``knn`` in the reference's dgcnn.model (already imported, or given). Returns True if patched."""
+def patch_dgcnn_knn(module=None, graph_feature: bool = False) -> bool:
+    """Rebinds ``knn`` in the reference's dgcnn.model (already imported, or given). Returns True if patched.
+    With ``graph_feature=True`` the module's ``get_graph_feature`` (src/dgcnn/model.py:23-42, looked up as a module
+    global by ``DGCNNfeat.forward``, :62-74) is replaced by the fused B200 version as well."""
     from ..knn import knn
+    from ..graph_feature import get_graph_feature
     mods = [module] if module is not None else [m for n, m in list(sys.modules.items())
                                                 if n in ("dgcnn.model", "src.dgcnn.model") and m is not None]
     done = False
     for m in mods:
         if hasattr(m, "knn") and hasattr(m, "get_graph_feature"):
             m.knn = knn
+            if graph_feature:
+                m.get_graph_feature = get_graph_feature
             done = True
     return done

@@ -17,6 +17,9 @@
  *       `.sum()` at src/models/few_shot.py:110,117.
  *   fpsg_knn_fwd
  *       `knn(x, k)` at src/dgcnn/model.py:13-20 (called from get_graph_feature, :28).
+ *   fpsg_edge_feature_fwd / fpsg_edge_feature_bwd
+ *       the gather / repeat / cat / permute tail of `get_graph_feature`, src/dgcnn/model.py:31-41, and its
+ *       autograd backward.
  *
  * INTEGRATION.md shows the reference-side bindings (ctypes) a maintainer would add.
  */
@@ -76,6 +79,18 @@ int fpsg_chamfer_loss_bwd(const float* p1, const float* p2, const int64_t* idx1,
 size_t fpsg_knn_workspace_bytes(int B, int C, int N, int k);
 int fpsg_knn_fwd(const float* x, int B, int C, int N, int k, int64_t* idx, void* ws, size_t ws_bytes,
                  fpsg_stream_t stream);
+
+/* ---- EdgeConv graph feature ------------------------------------------------------- */
+/* The tail of `get_graph_feature` (src/dgcnn/model.py:31-41): x (B,C,N), idx (B,N,k) int64 as knn returns it,
+ * out (B,2C,N,k): out[b,c,n,j] = x[b,c,idx[b,n,j]] - x[b,c,n] for c < C, out[b,C+c,n,j] = x[b,c,n].
+ * Every idx value must lie in [0, N). */
+int fpsg_edge_feature_fwd(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out,
+                          fpsg_stream_t stream);
+/* gout (B,2C,N,k) -> gx (B,C,N); gathers through an inverted index of idx built in the workspace (no
+ * floating-point atomics, double accumulation). */
+size_t fpsg_edge_feature_bwd_workspace_bytes(int B, int C, int N, int k);
+int fpsg_edge_feature_bwd(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws,
+                          size_t ws_bytes, fpsg_stream_t stream);
 
 /* ---- Profiling hooks (used by bench.py for the roofline line; not part of the reference-facing surface) ---- */
 /* Launches only K1's sweep kernel (the dominant kernel) with the workspace of fpsg_chamfer_fwd; the partial

@@ -38,3 +38,21 @@ def knn_torch(x: torch.Tensor, k: int) -> torch.Tensor:
     xx = torch.sum(x ** 2, dim=1, keepdim=True)                 # model.py:15
     pairwise_distance = -xx - inner - xx.transpose(2, 1)        # model.py:16
     return pairwise_distance.topk(k=k, dim=-1)[1]               # model.py:18
+
+
+def get_graph_feature_torch(x: torch.Tensor, k: int = 20, idx: torch.Tensor | None = None) -> torch.Tensor:
+    """Restatement of reference src/dgcnn/model.py:23-42 with the hard-coded ``torch.device('cuda')`` (:29)
+    replaced by ``x.device`` so that it also runs on CPU (the reference function itself cannot: it allocates
+    ``idx_base`` on 'cuda' unconditionally). Same tensor expressions otherwise; used as the autograd cross-check
+    and CPU statement of SURVEY.md 8f row f1."""
+    batch_size, num_dims, num_points = x.size()
+    x = x.view(batch_size, -1, num_points)                                            # model.py:25
+    if idx is None:
+        idx = knn_torch(x, k=k)                                                      # model.py:27-28
+    idx_base = torch.arange(0, batch_size, device=x.device).view(-1, 1, 1) * num_points  # model.py:31
+    idx = (idx + idx_base).view(-1)                                                   # model.py:33-34
+    x = x.transpose(2, 1).contiguous()                                                # model.py:36
+    feature = x.view(batch_size * num_points, -1)[idx, :]                             # model.py:37
+    feature = feature.view(batch_size, num_points, k, num_dims)                       # model.py:38
+    x = x.view(batch_size, num_points, 1, num_dims).repeat(1, 1, k, 1)                # model.py:39
+    return torch.cat((feature - x, x), dim=3).permute(0, 3, 1, 2).contiguous()        # model.py:41
