@@ -9,7 +9,9 @@
 // and the backward gathers through an inverted index of idx (built once per call with integer atomics, shared by all
 // channels) instead of scattering with floating-point atomics:
 //     gx[b,c,n] = sum_j (g[b,C+c,n,j] - g[b,c,n,j]) + sum_{(n',j): idx[b,n',j] = n} g[b,c,n',j]      (double accumulation)
-// Both kernels are HBM-bound: 8*C*N*k bytes written (forward) / read (backward) per cloud.
+// The forward is HBM-write-bound (8*C*N*k bytes per cloud); the backward reads as much but is bound by the random
+// gathers (one L1 wavefront per gathered element) -- shared-memory staging of the plane and shared-memory double
+// atomics were both tried in round 1 and were slower (uncoalesced list reads; 64-bit CAS loops).
 #include "common.cuh"
 
 namespace fpsg {
@@ -70,6 +72,7 @@ edge_invert_kernel(const int64_t* __restrict__ idx, int N, int k, int* __restric
 
     for (int n = tid; n <= N; n += 1024) sCnt[n] = 0;
     __syncthreads();
+#pragma unroll 8
     for (long long e = tid; e < nk; e += 1024) atomicAdd(&sCnt[(int)ib[e]], 1);
     __syncthreads();
     // exclusive scan over N counters, 1024 threads, chunked
@@ -106,6 +109,7 @@ edge_invert_kernel(const int64_t* __restrict__ idx, int N, int k, int* __restric
     }
     if (tid == 0) start[N] = carry;
     __syncthreads();
+#pragma unroll 8
     for (long long e = tid; e < nk; e += 1024) list[atomicAdd(&sCnt[(int)ib[e]], 1)] = (int)e;
 }
 
@@ -123,7 +127,17 @@ edge_feature_bwd_kernel(const float* __restrict__ g, const int* __restrict__ sta
     const int* __restrict__ list = list_all + (size_t)b * nk;
     double acc = 0.0;
     const long long e0 = (long long)n * k;
-    for (int j = 0; j < k; ++j) acc += (double)__ldcs(gm + e0 + j) - (double)__ldg(gd + e0 + j);
+    if ((k & 3) == 0 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+        // the point's k slots as 16-byte pieces: a quarter of the load instructions and L1 wavefronts
+        const float4* gm4 = reinterpret_cast<const float4*>(gm + e0);
+        const float4* gd4 = reinterpret_cast<const float4*>(gd + e0);
+        for (int j = 0; j < (k >> 2); ++j) {
+            const float4 m = __ldcs(gm4 + j), d = __ldg(gd4 + j);
+            acc += ((double)m.x - (double)d.x) + ((double)m.y - (double)d.y) + ((double)m.z - (double)d.z) + ((double)m.w - (double)d.w);
+        }
+    } else {
+        for (int j = 0; j < k; ++j) acc += (double)__ldcs(gm + e0 + j) - (double)__ldg(gd + e0 + j);
+    }
     const int s0 = start[n], s1 = start[n + 1];
     for (int s = s0; s < s1; s += 4) {
         float v[4];
