@@ -253,7 +253,7 @@ def main():
             pending[(i + 1) & 1].wait()
             pending[(i + 1) & 1] = None
 
-    kernels_per_step = 4  # sweep, finalize, loss, backward (the NCCL kernel for N > 1 is not ours)
+    kernels_per_step = 3  # sweep, finalize (+ fused loss), backward (the NCCL / torch.sum kernels for N > 1 are not ours)
 
     def barrier():
         if world > 1:

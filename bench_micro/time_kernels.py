@@ -41,7 +41,11 @@ for (B, C, N, k) in KN:
     nb = L.fpsg_knn_workspace_bytes(B, C, N, k); ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     f = lambda: _lib.check(L.fpsg_knn_fwd(x.data_ptr(), B, C, N, k, idx.data_ptr(), ws.data_ptr(), nb, s))
-    print(json.dumps({"knn": [B, C, N, k], "us": round(time_fn(f, 20, 3), 2)}))
+    def torch_knn():  # the reference's tensor expressions (src/dgcnn/model.py:14-18) on the same GPU, for scale
+        inner = -2 * torch.matmul(x.transpose(2, 1), x)
+        xx = torch.sum(x ** 2, dim=1, keepdim=True)
+        return (-xx - inner - xx.transpose(2, 1)).topk(k=k, dim=-1)[1]
+    print(json.dumps({"knn": [B, C, N, k], "us": round(time_fn(f, 20, 3), 2), "torch_reference_ops_us": round(time_fn(torch_knn, 10, 2), 2)}))
 
 import fpsg_b200
 for (B, C, N, k) in ([(32, 64, 1024, 20)] if "--c1" in sys.argv else [(32, 3, 1024, 20), (32, 64, 1024, 20), (32, 128, 1024, 20)]):
@@ -53,6 +57,12 @@ for (B, C, N, k) in ([(32, 64, 1024, 20)] if "--c1" in sys.argv else [(32, 3, 10
     g = lambda: _lib.check(L.fpsg_edge_feature_bwd(out.data_ptr(), idx.data_ptr(), B, C, N, k, gx.data_ptr(), ws.data_ptr(), nb, s))
     tf, tb = time_fn(f, 20, 3), time_fn(g, 20, 3)
     nbytes = 8.0 * C * N * k * B
-    from oracle.torch_formulation import get_graph_feature_torch
-    tt = time_fn(lambda: get_graph_feature_torch(x, k=k, idx=idx), 10, 2)
+    def torch_ops():  # the reference's tensor expressions (src/dgcnn/model.py:31-41) on the same GPU, for scale
+        base = torch.arange(0, B, device=x.device).view(-1, 1, 1) * N
+        flat = (idx + base).view(-1)
+        xt = x.transpose(2, 1).contiguous()
+        feat = xt.view(B * N, -1)[flat, :].view(B, N, k, C)
+        ctr = xt.view(B, N, 1, C).repeat(1, 1, k, 1)
+        return torch.cat((feat - ctr, ctr), dim=3).permute(0, 3, 1, 2).contiguous()
+    tt = time_fn(torch_ops, 10, 2)
     print(json.dumps({"edge_feature": [B, C, N, k], "fwd_us": round(tf, 1), "fwd_GBs": round(nbytes / tf / 1e3), "bwd_us": round(tb, 1), "bwd_GBs": round(nbytes / tb / 1e3), "torch_reference_ops_fwd_us": round(tt, 1)}))

@@ -37,7 +37,13 @@ def _check_clouds(p1: torch.Tensor, p2: torch.Tensor):
     return p1.contiguous(), p2.contiguous()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr(device) -> int:
+    """The current stream's cudaStream_t for `device` (the raw accessor is ~10x cheaper than building a Stream)."""
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(device).cuda_stream
 
 

@@ -10,8 +10,7 @@ from . import _lib
 from .knn import knn
 
 
-def _stream(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+from .chamfer import _stream_ptr as _stream
 
 
 class _GraphFeature(torch.autograd.Function):

@@ -6,6 +6,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
+from .chamfer import _stream_ptr
 
 
 def knn(x: torch.Tensor, k: int) -> torch.Tensor:
@@ -33,6 +34,6 @@ def knn(x: torch.Tensor, k: int) -> torch.Tensor:
         nbytes = L.fpsg_knn_workspace_bytes(B, C, N, k)
         ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=x.device)
         rc = L.fpsg_knn_fwd(x.data_ptr(), B, C, N, k, idx.data_ptr(), ws.data_ptr(), nbytes,
-                            torch.cuda.current_stream(x.device).cuda_stream)
+                            _stream_ptr(x.device))
         _lib.check(rc)
     return idx
