@@ -49,14 +49,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // loads the [C][jn] block x[:, j0:j0+jn] and the matching squared norms into shared memory (row stride J)
 __device__ __forceinline__ void knn_load_tile(float* sTile, float* sXX, const float* __restrict__ xb, const float* __restrict__ xxb,
-                                              int C, int N, int J, int j0, int jn, int tid) {
-    const int chunks = (jn + 31) >> 5;  // 32-column chunks per channel row
-    const int lane = tid & 31, w = tid >> 5;
-    for (int item = w; item < C * chunks; item += kKnnWarps) {
-        const int c = item / chunks, jj = (item - c * chunks) * 32 + lane;
-        if (jj < jn) cp_async_f32(sTile + (size_t)c * J + jj, xb + (size_t)c * N + j0 + jj);
+                                              int C, int N, int J, int j0, int jn, int tid, int nthreads = kKnnThreads) {
+    const int lane = tid & 31, w = tid >> 5, nwarps = nthreads >> 5;
+    for (int c = w; c < C; c += nwarps) {  // a warp copies whole channel rows: coalesced, no index arithmetic
+        const float* src = xb + (size_t)c * N + j0;
+        float* dst = sTile + (size_t)c * J;
+        for (int jj = lane; jj < jn; jj += 32) cp_async_f32(dst + jj, src + jj);
     }
-    for (int jj = tid; jj < jn; jj += kKnnThreads) cp_async_f32(sXX + jj, xxb + j0 + jj);
+    for (int jj = tid; jj < jn; jj += nthreads) cp_async_f32(sXX + jj, xxb + j0 + jj);
     cp_async_wait_all();
 }
 
@@ -479,8 +479,111 @@ knn_bulk_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
     }
 }
 
+// Generic channel count, k <= 32: the scoring is a register-tiled FP32 inner product. A warp owns 8 query points and
+// scores 128 candidates per step, 4 consecutive ones per lane: per channel one LDS.128 of candidates, two broadcast
+// LDS.128 of query values and 32 FFMAs -- six shared-memory wavefronts per 32 warp-FFMAs (the 32-candidate step of
+// knn_bulk_kernel needs three per 8). Selection is the bulk top-k above, one ballot per candidate slot.
+constexpr int kKnnTC = 4;  // candidates per lane per step
+constexpr int kGemmThreads = 512, kGemmWarps = kGemmThreads / 32;  // 16 warps share one candidate tile
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+knn_gemm_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int k, int J, int64_t* __restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sTile = reinterpret_cast<float*>(smem_raw);                 // [C][J], J a multiple of 128
+    float* sXX = sTile + (size_t)C * J;                                // [J]
+    float* sQ = sXX + J;                                               // [kGemmWarps][C][kKnnQB]
+    u64* sBuf = reinterpret_cast<u64*>(sQ + (size_t)kGemmWarps * C * kKnnQB);  // [kGemmWarps][kKnnQB][64]
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int b = blockIdx.y;
+    const int i0 = (blockIdx.x * kGemmWarps + w) * kKnnQB;
+    const float* __restrict__ xb = x + (size_t)b * C * N;
+    const float* __restrict__ xxb = xx + (size_t)b * N;
+    float* myQ = sQ + (size_t)w * C * kKnnQB;
+    u64* myBuf = sBuf + (size_t)w * kKnnQB * 64;
+
+    float xxi[kKnnQB], tau[kKnnQB];
+    u64 key[kKnnQB];
+    int cnt[kKnnQB];
+#pragma unroll
+    for (int q = 0; q < kKnnQB; ++q) {
+        xxi[q] = __ldg(xxb + min(i0 + q, N - 1));
+        tau[q] = -CUDART_INF_F;
+        key[q] = 0ull;
+        cnt[q] = 0;
+    }
+    for (int e = lane; e < C * kKnnQB; e += 32) {
+        const int c = e / kKnnQB, q = e - c * kKnnQB;
+        myQ[e] = __ldg(xb + (size_t)c * N + min(i0 + q, N - 1));
+    }
+    __syncwarp();
+
+    auto flush = [&](int q) {
+        key[q] = knn_flush_list(key[q], myBuf + q * 64, cnt[q]);
+        cnt[q] = 0;
+        const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(key[q] >> 32), k - 1);
+        tau[q] = hi ? ord_to_f32(hi) : -CUDART_INF_F;
+    };
+
+    for (int j0 = 0; j0 < N; j0 += J) {
+        const int jn = min(J, N - j0);
+        __syncthreads();  // previous tile fully consumed
+        knn_load_tile(sTile, sXX, xb, xxb, C, N, J, j0, jn, tid, kGemmThreads);
+        __syncthreads();
+        if (i0 >= N) continue;  // warp-uniform; the warp still takes part in the barriers
+
+        for (int jb = 0; jb < jn; jb += 32 * kKnnTC) {
+            const int jl = jb + kKnnTC * lane;  // this lane's first candidate inside the tile
+            float dot[kKnnQB][kKnnTC];
+#pragma unroll
+            for (int q = 0; q < kKnnQB; ++q)
+#pragma unroll
+                for (int t = 0; t < kKnnTC; ++t) dot[q][t] = 0.f;
+            const float* tp = sTile + jl;
+#pragma unroll 2
+            for (int c = 0; c < C; ++c) {
+                const float4 cv = *reinterpret_cast<const float4*>(tp + (size_t)c * J);
+                const float4 qa = *reinterpret_cast<const float4*>(myQ + c * kKnnQB);
+                const float4 qb = *reinterpret_cast<const float4*>(myQ + c * kKnnQB + 4);
+                const float qv[kKnnQB] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                const float cc[kKnnTC] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                for (int q = 0; q < kKnnQB; ++q)
+#pragma unroll
+                    for (int t = 0; t < kKnnTC; ++t) dot[q][t] = __fmaf_rn(qv[q], cc[t], dot[q][t]);
+            }
+            const float4 nx = *reinterpret_cast<const float4*>(sXX + jl);
+            const float nxx[kKnnTC] = {-nx.x, -nx.y, -nx.z, -nx.w};
+#pragma unroll
+            for (int t = 0; t < kKnnTC; ++t) {
+                const bool inb = jl + t < jn;
+                const unsigned jkey = 0xffffffffu - (unsigned)(j0 + jl + t);
+#pragma unroll
+                for (int q = 0; q < kKnnQB; ++q) {
+                    const float pd = __fsub_rn(__fmaf_rn(2.0f, dot[q][t], nxx[t]), xxi[q]);
+                    const bool pass = inb && pd > tau[q];
+                    const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                    if (mask) {  // warp-uniform
+                        if (pass) myBuf[q * 64 + cnt[q] + __popc(mask & lt_mask)] = ((u64)f32_to_ord(pd) << 32) | jkey;
+                        cnt[q] += __popc(mask);
+                        if (cnt[q] >= 32) flush(q);
+                    }
+                }
+            }
+        }
+    }
+    if (i0 >= N) return;
+#pragma unroll
+    for (int q = 0; q < kKnnQB; ++q) {
+        if (cnt[q] > 0) flush(q);
+        if (i0 + q < N && lane < k) idx[((size_t)b * N + i0 + q) * k + lane] = (int64_t)(0xffffffffu - (unsigned)key[q]);
+    }
+}
+
 struct KnnPlan {
     int KR;
+    bool gemm;  // generic C, k <= 32: the register-tiled scoring kernel
     int J;
     size_t smem;
     size_t ws_bytes;
@@ -495,6 +598,21 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
     const int npad = (N + 31) / 32 * 32;
     if (j > npad) j = npad;
     p.J = (int)j;
+    p.gemm = false;
+    if (p.KR == 1 && C != 3 && !getenv("FPSG_KNN_INSERT") && !getenv("FPSG_KNN_NOGEMM")) {
+        long long jg = (long long)(kKnnTileBytes / sizeof(float)) / (C + 1) / 128 * 128;
+        if (jg < 128) jg = 128;
+        const long long npad128 = (N + 127) / 128 * 128;
+        if (jg > npad128) jg = npad128;
+        const size_t smem = ((size_t)C * jg + jg + (size_t)kGemmWarps * C * kKnnQB) * sizeof(float) + (size_t)kGemmWarps * kKnnQB * 64 * sizeof(u64);
+        if (smem <= 220 * 1024) {
+            p.gemm = true;
+            p.J = (int)jg;
+            p.smem = smem;
+            p.ws_bytes = align_up((size_t)B * N * sizeof(float), 256);
+            return p;
+        }
+    }
     if (p.KR == 1 && !getenv("FPSG_KNN_INSERT"))  // bulk top-k kernel: tile + (generic C) query values + candidate buffers
         p.smem = ((size_t)C * p.J + p.J + (C == 3 ? 0 : (size_t)kKnnWarps * C * kKnnQB)) * sizeof(float) + (size_t)kKnnWarps * kKnnQB * 64 * sizeof(u64);
     else if (C == 3)
@@ -508,6 +626,14 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
 size_t knn_workspace(int B, int C, int N, int k) {
     if (B <= 0 || C < 1 || N < 1 || k < 1) return 0;
     return make_knn_plan(B, C, N, k).ws_bytes;
+}
+
+static int knn_launch_gemm(const float* x, const float* xx, int B, int C, int N, int k, const KnnPlan& p, int64_t* idx, cudaStream_t stream) {
+    if (p.smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(knn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    const dim3 grid((unsigned)cdiv(N, kGemmWarps * kKnnQB), (unsigned)B);
+    knn_gemm_kernel<<<grid, kGemmThreads, p.smem, stream>>>(x, xx, C, N, k, p.J, idx);
+    FPSG_CUDA_OK(cudaGetLastError());
+    return FPSG_OK;
 }
 
 template <bool C3>
@@ -558,6 +684,7 @@ int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx,
         case 1:
             if (getenv("FPSG_KNN_INSERT"))  // tuning override: the shuffle-insertion kernels also serve k <= 32
                 return c3 ? knn_launch_t<1, true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_blocked<1>(x, xx, B, C, N, k, p, idx, stream);
+            if (p.gemm) return knn_launch_gemm(x, xx, B, C, N, k, p, idx, stream);
             return c3 ? knn_launch_bulk<true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_bulk<false>(x, xx, B, C, N, k, p, idx, stream);
         case 2:
             return c3 ? knn_launch_t<2, true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_blocked<2>(x, xx, B, C, N, k, p, idx, stream);
