@@ -581,6 +581,199 @@ knn_gemm_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// C = 3, k <= 32: two-pass selection, one query per thread (the DGCNN xyz layer, BASELINE config c3).
+//
+// The whole cloud sits in shared memory as (x, y, z, -xx) and every lane of a warp reads the same candidate
+// (broadcast LDS.128), so scoring has no shuffles, no ballots and no divergence:
+//   pass 1  score all N candidates, keep only the maximum of each of 32 contiguous candidate groups. The k-th
+//           largest group maximum T is a lower bound of the k-th largest score: k different candidates reach it.
+//           (a 32-input sorting network over the thread's own group maxima; about 31 candidates reach T for
+//           k = 20, N = 1024.)
+//   pass 2  score again and append -- branch-free: unconditional 16-bit store, conditional cursor bump -- the
+//           index of every candidate with pd >= T to the thread's own column of a shared-memory buffer.
+//   final   each warp sorts the short list of each of its 32 queries on (order-preserving pd bits, ~index)
+//           keys with a bitonic network and writes the first k indices.
+// A query whose list would overflow the buffer (heavily duplicated points: everything ties with T) is redone by
+// its warp with a streaming sort-and-merge over all N candidates, so the result is exact for any input.
+// pd is computed by the same instruction sequence everywhere (see the file header), so the three stages agree
+// bit for bit. Padded candidates carry NaN in .w: their pd is NaN, max.f32 ignores it and `>=` rejects it.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSelGroups = 32;                 // candidate groups (>= k)
+constexpr int kSelCap = 64;                    // list slots per query
+constexpr int kSelGuard = 8;                   // candidates between two overflow checks
+constexpr int kSelListStride = kSelCap + 2;    // u16 elements per row of the per-query lists (conflict-free both ways)
+constexpr int kSelMaxN = 8192;                 // the cloud must fit shared memory as float4
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+__device__ __forceinline__ float knn_pd3(const float4 q, const float xxi, const float4 c) {
+    float dot = __fmul_rn(q.x, c.x);
+    dot = __fmaf_rn(q.y, c.y, dot);
+    dot = __fmaf_rn(q.z, c.z, dot);
+    return __fsub_rn(__fmaf_rn(2.0f, dot, c.w), xxi);
+}
+
+__device__ __forceinline__ u64 knn_key3(const float4 q, const float xxi, const float4 c, int j) {
+    return ((u64)f32_to_ord(knn_pd3(q, xxi, c)) << 32) | (u64)(0xffffffffu - (unsigned)j);
+}
+
+size_t knn_select_smem(int N, int threads) {
+    const int gs = cdiv(N, kSelGroups);
+    return (size_t)gs * kSelGroups * sizeof(float4) + (size_t)kSelGroups * threads * sizeof(float) +
+           (size_t)kSelCap * threads * sizeof(unsigned short) + (size_t)threads * kSelListStride * sizeof(unsigned short) +
+           (size_t)threads * sizeof(int);
+}
+
+__global__ void __launch_bounds__(256)
+knn_select_kernel(const float* __restrict__ x, int N, int k, int gs, int64_t* __restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x;
+    const int npad = gs * kSelGroups;
+    float4* sTile = reinterpret_cast<float4*>(smem_raw);                               // [npad] (x, y, z, -xx)
+    float* sGm = reinterpret_cast<float*>(sTile + npad);                               // [32][T] group maxima
+    unsigned short* sBuf = reinterpret_cast<unsigned short*>(sGm + kSelGroups * T);    // [cap][T] pass-2 columns
+    unsigned short* sList = sBuf + kSelCap * T;                                        // [T][stride] lists, row per query
+    int* sCnt = reinterpret_cast<int*>(sList + T * kSelListStride);                    // [T] list length, -1 = overflow
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int b = blockIdx.y;
+    const float* __restrict__ xb = x + (size_t)b * 3 * N;
+
+    // the cloud and its squared norms (xx = rn(rn(x0^2 + x1^2) + x2^2), model.py:15)
+    for (int j = tid; j < npad; j += T) {
+        float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));
+        if (j < N) {
+            v.x = __ldg(xb + j);
+            v.y = __ldg(xb + (size_t)N + j);
+            v.z = __ldg(xb + 2 * (size_t)N + j);
+            v.w = -__fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z));
+        }
+        sTile[j] = v;
+    }
+    __syncthreads();
+
+    const int i = blockIdx.x * T + tid;
+    const float4 q = sTile[min(i, N - 1)];  // rows past N are clamped: computed, never written
+    const float xxi = -q.w;
+
+    // ---- pass 1: group maxima ----
+    for (int g = 0; g < kSelGroups; ++g) {
+        const float4* tp = sTile + g * gs;
+        float a0 = -CUDART_INF_F, a1 = -CUDART_INF_F;
+        int jj = 0;
+#pragma unroll 2
+        for (; jj + 4 <= gs; jj += 4) {
+            const float p0 = knn_pd3(q, xxi, tp[jj]), p1 = knn_pd3(q, xxi, tp[jj + 1]);
+            const float p2 = knn_pd3(q, xxi, tp[jj + 2]), p3 = knn_pd3(q, xxi, tp[jj + 3]);
+            a0 = max3(a0, p0, p1);
+            a1 = max3(a1, p2, p3);
+        }
+        for (; jj < gs; ++jj) a0 = max3(a0, a0, knn_pd3(q, xxi, tp[jj]));
+        sGm[g * T + tid] = max3(a0, a0, a1);
+    }
+
+    // ---- threshold: k-th largest group maximum (bitonic network over the thread's own 32 values) ----
+    float thr;
+    {
+        float v[kSelGroups];
+#pragma unroll
+        for (int g = 0; g < kSelGroups; ++g) v[g] = sGm[g * T + tid];
+#pragma unroll
+        for (int s = 2; s <= kSelGroups; s <<= 1) {
+#pragma unroll
+            for (int d = s >> 1; d > 0; d >>= 1) {
+#pragma unroll
+                for (int e = 0; e < kSelGroups; ++e) {
+                    const int p = e ^ d;
+                    if (p > e) {
+                        const bool desc = (s == kSelGroups) || ((e & s) == 0);
+                        const float hi = fmaxf(v[e], v[p]), lo = fminf(v[e], v[p]);
+                        v[e] = desc ? hi : lo;
+                        v[p] = desc ? lo : hi;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kSelGroups; ++g) sGm[g * T + tid] = v[g];
+        thr = sGm[(k - 1) * T + tid];
+    }
+
+    // ---- pass 2: indices of all candidates with pd >= thr, into this thread's column of sBuf ----
+    int cnt;
+    {
+        const unsigned stepb = 2u * T;
+        unsigned char* col = reinterpret_cast<unsigned char*>(sBuf) + 2 * tid;
+        unsigned off = 0;
+        const unsigned limit = (kSelCap - kSelGuard) * stepb;
+        bool ovf = false;
+        for (int j = 0; j < npad; j += kSelGuard) {
+#pragma unroll
+            for (int u = 0; u < kSelGuard; ++u) {
+                const float pd = knn_pd3(q, xxi, sTile[j + u]);
+                *reinterpret_cast<unsigned short*>(col + off) = (unsigned short)(j + u);
+                off += pd >= thr ? stepb : 0u;
+            }
+            if (off > limit) {
+                ovf = true;
+                off = limit;
+            }
+        }
+        cnt = ovf ? -1 : (int)(off / stepb);
+    }
+    for (int e = 0; e < cnt; ++e) sList[tid * kSelListStride + e] = sBuf[e * T + tid];
+    sCnt[tid] = cnt;
+    __syncwarp();
+
+    // ---- final: the warp sorts each of its 32 queries' lists ----
+    for (int qq = 0; qq < 32; ++qq) {
+        const int t = w * 32 + qq;
+        const int iq = blockIdx.x * T + t;
+        if (iq >= N) break;  // warp-uniform
+        const int c = sCnt[t];
+        const float4 qp = sTile[iq];
+        const float qxx = -qp.w;
+        u64 key = 0ull;
+        if (c >= 0) {
+            for (int h = 0; h * 32 < c; ++h) {
+                const int e = h * 32 + lane;
+                u64 kb = 0ull;
+                if (e < c) {
+                    const int j = sList[t * kSelListStride + e];
+                    kb = knn_key3(qp, qxx, sTile[j], j);
+                }
+                kb = warp_sort_desc(kb, lane);
+                if (h == 0) {
+                    key = kb;
+                } else {
+                    const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
+                    key = warp_merge_desc(key > rev ? key : rev, lane);
+                }
+            }
+        } else {
+            // overflow: streaming sort-and-merge over the whole cloud
+            u64 tau = 0ull;
+            for (int j0 = 0; j0 < N; j0 += 32) {
+                const int j = j0 + lane;
+                u64 kb = j < N ? knn_key3(qp, qxx, sTile[j], j) : 0ull;
+                if (!(kb > tau)) kb = 0ull;
+                if (__any_sync(0xffffffffu, kb != 0ull)) {
+                    kb = warp_sort_desc(kb, lane);
+                    const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
+                    key = warp_merge_desc(key > rev ? key : rev, lane);
+                    tau = __shfl_sync(0xffffffffu, key, k - 1);
+                }
+            }
+        }
+        if (lane < k) idx[((size_t)b * N + iq) * k + lane] = (int64_t)(0xffffffffu - (unsigned)key);
+    }
+}
+
 struct KnnPlan {
     int KR;
     bool gemm;  // generic C, k <= 32: the register-tiled scoring kernel
@@ -676,6 +869,14 @@ int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx,
     if ((size_t)C * 32 * sizeof(float) > 160 * 1024) return fail(FPSG_EINVAL, "knn: C=%d too large", C);
     const KnnPlan p = make_knn_plan(B, C, N, k);
     if (!ws || ws_bytes < p.ws_bytes) return fail(FPSG_EWORKSPACE, "knn: workspace of %zu bytes required, %zu given", p.ws_bytes, ws ? ws_bytes : (size_t)0);
+    if (C == 3 && k <= 32 && N <= kSelMaxN && !getenv("FPSG_KNN_BULK")) {  // two-pass selection kernel (needs no workspace)
+        const int threads = N <= 2048 ? 128 : 256;
+        const size_t smem = knn_select_smem(N, threads);
+        if (smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_select_kernel<<<dim3((unsigned)cdiv(N, threads), (unsigned)B), threads, smem, stream>>>(x, N, k, cdiv(N, kSelGroups), idx);
+        FPSG_CUDA_OK(cudaGetLastError());
+        return FPSG_OK;
+    }
     float* xx = static_cast<float*>(ws);
     knn_sqnorm_kernel<<<dim3((unsigned)cdiv(N, 256), (unsigned)B), 256, 0, stream>>>(x, C, N, xx);
     FPSG_CUDA_OK(cudaGetLastError());
