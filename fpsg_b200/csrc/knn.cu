@@ -622,25 +622,63 @@ __device__ __forceinline__ u64 knn_key3(const float4 q, const float xxi, const f
     return ((u64)f32_to_ord(knn_pd3(q, xxi, c)) << 32) | (u64)(0xffffffffu - (unsigned)j);
 }
 
-size_t knn_select_smem(int N, int threads) {
-    const int gs = cdiv(N, kSelGroups);
-    return (size_t)gs * kSelGroups * sizeof(float4) + (size_t)kSelGroups * threads * sizeof(float) +
-           (size_t)kSelCap * threads * sizeof(unsigned short) + (size_t)threads * kSelListStride * sizeof(unsigned short) +
-           (size_t)threads * sizeof(int);
+// sorts two independent key sets at once (the two shuffle chains overlap: the stage is latency-bound otherwise)
+__device__ __forceinline__ void warp_sort_desc2(u64& a, u64& b, int lane) {
+#pragma unroll
+    for (int s = 2; s <= 32; s <<= 1) {
+        const bool desc = s == 32 ? true : ((lane & s) == 0);
+#pragma unroll
+        for (int d = s >> 1; d > 0; d >>= 1) {
+            const bool tm = ((lane & d) == 0) == desc;
+            a = key_cmpx(a, d, tm);
+            b = key_cmpx(b, d, tm);
+        }
+    }
+}
+__device__ __forceinline__ void warp_merge_desc2(u64& a, u64& b, int lane) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a = key_cmpx(a, d, (lane & d) == 0);
+        b = key_cmpx(b, d, (lane & d) == 0);
+    }
 }
 
+// S = threads (in S different warps) that share one query: each scans 1/S of the candidates in both passes
+struct KnnSelSmem {
+    size_t tile, gm, thr, buf, list, cntp, cnt, total;
+};
+static KnnSelSmem knn_select_layout(int N, int threads, int S) {
+    const int gs = cdiv(N, kSelGroups), Q = threads / S;
+    KnnSelSmem L;
+    size_t off = 0;
+    L.tile = off; off += (size_t)gs * kSelGroups * sizeof(float4);
+    L.gm = off;   off += (size_t)kSelGroups * Q * sizeof(float);
+    L.thr = off;  off += (size_t)Q * sizeof(float);
+    L.cntp = off; off += (size_t)threads * sizeof(int);
+    L.cnt = off;  off += (size_t)Q * sizeof(int);
+    L.buf = off;  off += (size_t)kSelCap * threads * sizeof(unsigned short);
+    L.list = off; off += (size_t)Q * kSelListStride * sizeof(unsigned short);
+    L.total = align_up(off, 16);
+    return L;
+}
+
+template <int S>
 __global__ void __launch_bounds__(256)
-knn_select_kernel(const float* __restrict__ x, int N, int k, int gs, int64_t* __restrict__ idx) {
+knn_select_kernel(const float* __restrict__ x, int N, int k, int gs, int64_t* __restrict__ idx, const KnnSelSmem L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = blockDim.x;
+    const int T = blockDim.x, Q = T / S;
     const int npad = gs * kSelGroups;
-    float4* sTile = reinterpret_cast<float4*>(smem_raw);                               // [npad] (x, y, z, -xx)
-    float* sGm = reinterpret_cast<float*>(sTile + npad);                               // [32][T] group maxima
-    unsigned short* sBuf = reinterpret_cast<unsigned short*>(sGm + kSelGroups * T);    // [cap][T] pass-2 columns
-    unsigned short* sList = sBuf + kSelCap * T;                                        // [T][stride] lists, row per query
-    int* sCnt = reinterpret_cast<int*>(sList + T * kSelListStride);                    // [T] list length, -1 = overflow
+    float4* sTile = reinterpret_cast<float4*>(smem_raw + L.tile);                  // [npad] (x, y, z, -xx)
+    float* sGm = reinterpret_cast<float*>(smem_raw + L.gm);                        // [32][Q] group maxima
+    float* sThr = reinterpret_cast<float*>(smem_raw + L.thr);                      // [Q]
+    int* sCntP = reinterpret_cast<int*>(smem_raw + L.cntp);                        // [T] pass-2 count of each thread, -1 = overflow
+    int* sCnt = reinterpret_cast<int*>(smem_raw + L.cnt);                          // [Q] list length, -1 = overflow
+    unsigned short* sBuf = reinterpret_cast<unsigned short*>(smem_raw + L.buf);    // [cap][T] pass-2 columns
+    unsigned short* sList = reinterpret_cast<unsigned short*>(smem_raw + L.list);  // [Q][stride] one row per query
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int wq = w / S, part = w - wq * S;  // the S warps wq*S .. wq*S+S-1 share 32 queries
+    const int ql = wq * 32 + lane;            // query of this thread inside the CTA
     const int b = blockIdx.y;
     const float* __restrict__ xb = x + (size_t)b * 3 * N;
 
@@ -657,32 +695,36 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int gs, int64_t* __
     }
     __syncthreads();
 
-    const int i = blockIdx.x * T + tid;
+    const int i = blockIdx.x * Q + ql;
     const float4 q = sTile[min(i, N - 1)];  // rows past N are clamped: computed, never written
     const float xxi = -q.w;
+    constexpr int kGroupsPerPart = kSelGroups / S;
 
-    // ---- pass 1: group maxima ----
-    for (int g = 0; g < kSelGroups; ++g) {
+    // ---- pass 1: group maxima of this thread's share of the candidates ----
+#pragma unroll 1
+    for (int g = part * kGroupsPerPart; g < (part + 1) * kGroupsPerPart; ++g) {
         const float4* tp = sTile + g * gs;
-        float a0 = -CUDART_INF_F, a1 = -CUDART_INF_F;
+        float a0 = -CUDART_INF_F, a1 = -CUDART_INF_F, a2 = -CUDART_INF_F, a3 = -CUDART_INF_F;
         int jj = 0;
-#pragma unroll 2
-        for (; jj + 4 <= gs; jj += 4) {
-            const float p0 = knn_pd3(q, xxi, tp[jj]), p1 = knn_pd3(q, xxi, tp[jj + 1]);
-            const float p2 = knn_pd3(q, xxi, tp[jj + 2]), p3 = knn_pd3(q, xxi, tp[jj + 3]);
-            a0 = max3(a0, p0, p1);
-            a1 = max3(a1, p2, p3);
+        for (; jj + 8 <= gs; jj += 8) {
+            float p[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) p[u] = knn_pd3(q, xxi, tp[jj + u]);
+            a0 = max3(a0, p[0], p[1]);
+            a1 = max3(a1, p[2], p[3]);
+            a2 = max3(a2, p[4], p[5]);
+            a3 = max3(a3, p[6], p[7]);
         }
         for (; jj < gs; ++jj) a0 = max3(a0, a0, knn_pd3(q, xxi, tp[jj]));
-        sGm[g * T + tid] = max3(a0, a0, a1);
+        sGm[g * Q + ql] = max3(max3(a0, a0, a1), a2, a3);
     }
+    if (S > 1) __syncthreads();
 
-    // ---- threshold: k-th largest group maximum (bitonic network over the thread's own 32 values) ----
-    float thr;
-    {
+    // ---- threshold: k-th largest group maximum (bitonic network over the query's 32 values) ----
+    if (part == 0) {
         float v[kSelGroups];
 #pragma unroll
-        for (int g = 0; g < kSelGroups; ++g) v[g] = sGm[g * T + tid];
+        for (int g = 0; g < kSelGroups; ++g) v[g] = sGm[g * Q + ql];
 #pragma unroll
         for (int s = 2; s <= kSelGroups; s <<= 1) {
 #pragma unroll
@@ -700,78 +742,138 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int gs, int64_t* __
             }
         }
 #pragma unroll
-        for (int g = 0; g < kSelGroups; ++g) sGm[g * T + tid] = v[g];
-        thr = sGm[(k - 1) * T + tid];
+        for (int g = 0; g < kSelGroups; ++g) sGm[g * Q + ql] = v[g];
+        sThr[ql] = sGm[(k - 1) * Q + ql];
     }
+    if (S > 1) __syncthreads();
+    const float thr = sThr[ql];
 
-    // ---- pass 2: indices of all candidates with pd >= thr, into this thread's column of sBuf ----
-    int cnt;
+    // ---- pass 2: indices of this share's candidates with pd >= thr, into this thread's column of sBuf ----
+    // (inline PTX: an unconditional 16-bit store at the cursor and a predicated cursor bump -- no select, no branch)
     {
+        const unsigned col = static_cast<unsigned>(__cvta_generic_to_shared(sBuf + tid));
         const unsigned stepb = 2u * T;
-        unsigned char* col = reinterpret_cast<unsigned char*>(sBuf) + 2 * tid;
-        unsigned off = 0;
-        const unsigned limit = (kSelCap - kSelGuard) * stepb;
+        const unsigned limit = col + (kSelCap - kSelGuard) * stepb;
+        unsigned p = col;
         bool ovf = false;
-        for (int j = 0; j < npad; j += kSelGuard) {
+        const int jbeg = part * kGroupsPerPart * gs, jend = jbeg + kGroupsPerPart * gs;  // a multiple of 8 candidates
+#pragma unroll 1
+        for (int j = jbeg; j < jend; j += kSelGuard) {
 #pragma unroll
             for (int u = 0; u < kSelGuard; ++u) {
                 const float pd = knn_pd3(q, xxi, sTile[j + u]);
-                *reinterpret_cast<unsigned short*>(col + off) = (unsigned short)(j + u);
-                off += pd >= thr ? stepb : 0u;
+                const unsigned short jv = (unsigned short)(j + u);
+                asm volatile(
+                    "{\n\t.reg .pred pp;\n\t"
+                    "st.shared.u16 [%0], %1;\n\t"
+                    "setp.ge.f32 pp, %2, %3;\n\t"
+                    "@pp add.u32 %0, %0, %4;\n\t}"
+                    : "+r"(p)
+                    : "h"(jv), "f"(pd), "f"(thr), "r"(stepb)
+                    : "memory");
             }
-            if (off > limit) {
+            if (p > limit) {
                 ovf = true;
-                off = limit;
+                p = limit;
             }
         }
-        cnt = ovf ? -1 : (int)(off / stepb);
+        sCntP[tid] = ovf ? -1 : (int)((p - col) / stepb);
     }
-    for (int e = 0; e < cnt; ++e) sList[tid * kSelListStride + e] = sBuf[e * T + tid];
-    sCnt[tid] = cnt;
-    __syncwarp();
+    if (S > 1) __syncthreads(); else __syncwarp();
 
-    // ---- final: the warp sorts each of its 32 queries' lists ----
-    for (int qq = 0; qq < 32; ++qq) {
-        const int t = w * 32 + qq;
-        const int iq = blockIdx.x * T + t;
-        if (iq >= N) break;  // warp-uniform
-        const int c = sCnt[t];
-        const float4 qp = sTile[iq];
-        const float qxx = -qp.w;
-        u64 key = 0ull;
-        if (c >= 0) {
-            for (int h = 0; h * 32 < c; ++h) {
-                const int e = h * 32 + lane;
-                u64 kb = 0ull;
-                if (e < c) {
-                    const int j = sList[t * kSelListStride + e];
-                    kb = knn_key3(qp, qxx, sTile[j], j);
-                }
-                kb = warp_sort_desc(kb, lane);
-                if (h == 0) {
-                    key = kb;
-                } else {
-                    const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
-                    key = warp_merge_desc(key > rev ? key : rev, lane);
+    // ---- the S shares of a query, concatenated into its row of sList ----
+    {
+        int before = 0, total = 0;
+        bool ovf = false;
+#pragma unroll
+        for (int pp = 0; pp < S; ++pp) {
+            const int c = sCntP[(wq * S + pp) * 32 + lane];
+            ovf |= c < 0;
+            if (pp < part) before += c;
+            total += c;
+        }
+        ovf |= total > kSelCap;
+        if (!ovf) {
+            const int mine = sCntP[tid];
+            for (int e = 0; e < mine; ++e) sList[ql * kSelListStride + before + e] = sBuf[e * T + tid];
+        }
+        if (part == 0) sCnt[ql] = ovf ? -1 : total;
+    }
+    if (S > 1) __syncthreads(); else __syncwarp();
+
+    // ---- final: the warp sorts the lists of its queries, two at a time, and writes the first k indices ----
+    constexpr int kPerWarp = 32 / S;  // queries of the group this warp finishes: part, part + S, ...
+#pragma unroll 1
+    for (int n = 0; n < kPerWarp; n += 2) {
+        int tq[2], iq[2], c[2];
+        float4 qp[2];
+        u64 key[2];
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+            tq[z] = wq * 32 + part + (n + z) * S;
+            iq[z] = blockIdx.x * Q + tq[z];
+            const bool live = (n + z) < kPerWarp && iq[z] < N;
+            c[z] = live ? sCnt[tq[z]] : 0;
+            qp[z] = sTile[min(iq[z], N - 1)];
+            key[z] = 0ull;
+            if (!live) iq[z] = -1;
+        }
+        const int rounds = max((max(c[0], c[1]) + 31) >> 5, 0);
+#pragma unroll 1
+        for (int h = 0; h < rounds; ++h) {
+            const int e = h * 32 + lane;
+            u64 kb[2];
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                kb[z] = 0ull;
+                if (e < c[z]) {
+                    const int j = sList[tq[z] * kSelListStride + e];
+                    kb[z] = knn_key3(qp[z], -qp[z].w, sTile[j], j);
                 }
             }
-        } else {
-            // overflow: streaming sort-and-merge over the whole cloud
-            u64 tau = 0ull;
-            for (int j0 = 0; j0 < N; j0 += 32) {
-                const int j = j0 + lane;
-                u64 kb = j < N ? knn_key3(qp, qxx, sTile[j], j) : 0ull;
-                if (!(kb > tau)) kb = 0ull;
-                if (__any_sync(0xffffffffu, kb != 0ull)) {
-                    kb = warp_sort_desc(kb, lane);
-                    const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
-                    key = warp_merge_desc(key > rev ? key : rev, lane);
-                    tau = __shfl_sync(0xffffffffu, key, k - 1);
-                }
+            warp_sort_desc2(kb[0], kb[1], lane);
+            if (h == 0) {
+                key[0] = kb[0];
+                key[1] = kb[1];
+            } else {
+                const u64 r0 = __shfl_sync(0xffffffffu, kb[0], 31 - lane), r1 = __shfl_sync(0xffffffffu, kb[1], 31 - lane);
+                key[0] = key[0] > r0 ? key[0] : r0;
+                key[1] = key[1] > r1 ? key[1] : r1;
+                warp_merge_desc2(key[0], key[1], lane);
             }
         }
-        if (lane < k) idx[((size_t)b * N + iq) * k + lane] = (int64_t)(0xffffffffu - (unsigned)key);
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+            if (iq[z] < 0) continue;  // warp-uniform
+            if (c[z] < 0) {
+                // overflow: streaming sort-and-merge over the whole cloud
+                u64 kk = 0ull, tau = 0ull;
+                for (int j0 = 0; j0 < N; j0 += 32) {
+                    const int j = j0 + lane;
+                    u64 kb = j < N ? knn_key3(qp[z], -qp[z].w, sTile[j], j) : 0ull;
+                    if (!(kb > tau)) kb = 0ull;
+                    if (__any_sync(0xffffffffu, kb != 0ull)) {
+                        kb = warp_sort_desc(kb, lane);
+                        const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
+                        kk = warp_merge_desc(kk > rev ? kk : rev, lane);
+                        tau = __shfl_sync(0xffffffffu, kk, k - 1);
+                    }
+                }
+                key[z] = kk;
+            }
+            if (lane < k) idx[((size_t)b * N + iq[z]) * k + lane] = (int64_t)(0xffffffffu - (unsigned)key[z]);
+        }
     }
+}
+
+static int sm_count_knn() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else return 148;
+    }
+    return n;
 }
 
 struct KnnPlan {
@@ -870,10 +972,18 @@ int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx,
     const KnnPlan p = make_knn_plan(B, C, N, k);
     if (!ws || ws_bytes < p.ws_bytes) return fail(FPSG_EWORKSPACE, "knn: workspace of %zu bytes required, %zu given", p.ws_bytes, ws ? ws_bytes : (size_t)0);
     if (C == 3 && k <= 32 && N <= kSelMaxN && !getenv("FPSG_KNN_BULK")) {  // two-pass selection kernel (needs no workspace)
-        const int threads = N <= 2048 ? 128 : 256;
-        const size_t smem = knn_select_smem(N, threads);
-        if (smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_select_kernel<<<dim3((unsigned)cdiv(N, threads), (unsigned)B), threads, smem, stream>>>(x, N, k, cdiv(N, kSelGroups), idx);
+        // S warps share 32 queries so that even a small batch fills the chip: aim at >= 4 warps per SM sub-partition
+        const long long qwarps = (long long)B * cdiv(N, 32);
+        int S = qwarps >= 4LL * 4 * sm_count_knn() ? 1 : (qwarps * 2 >= 4LL * 4 * sm_count_knn() ? 2 : 4);
+        if (const char* e = getenv("FPSG_KNN_SPLIT")) {  // tuning override: 1, 2 or 4
+            const int v = atoi(e);
+            if (v == 1 || v == 2 || v == 4) S = v;
+        }
+        const int threads = 256;
+        const KnnSelSmem L = knn_select_layout(N, threads, S);
+        auto kern = S == 1 ? knn_select_kernel<1> : (S == 2 ? knn_select_kernel<2> : knn_select_kernel<4>);
+        if (L.total > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        kern<<<dim3((unsigned)cdiv(N, threads / S), (unsigned)B), threads, L.total, stream>>>(x, N, k, cdiv(N, kSelGroups), idx, L);
         FPSG_CUDA_OK(cudaGetLastError());
         return FPSG_OK;
     }
