@@ -582,28 +582,35 @@ knn_gemm_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// C = 3, k <= 32: two-pass selection, one query per thread (the DGCNN xyz layer, BASELINE config c3).
+// C = 3, k <= 32: threshold selection (the DGCNN xyz layer, BASELINE config c3).
 //
-// The whole cloud sits in shared memory as (x, y, z, -xx) and every lane of a warp reads the same candidate
-// (broadcast LDS.128), so scoring has no shuffles, no ballots and no divergence:
-//   pass 1  score all N candidates, keep only the maximum of each of 32 contiguous candidate groups. The k-th
-//           largest group maximum T is a lower bound of the k-th largest score: k different candidates reach it.
-//           (a 32-input sorting network over the thread's own group maxima; about 31 candidates reach T for
-//           k = 20, N = 1024.)
-//   pass 2  score again and append -- branch-free: unconditional 16-bit store, conditional cursor bump -- the
-//           index of every candidate with pd >= T to the thread's own column of a shared-memory buffer.
-//   final   each warp sorts the short list of each of its 32 queries on (order-preserving pd bits, ~index)
-//           keys with a bitonic network and writes the first k indices.
-// A query whose list would overflow the buffer (heavily duplicated points: everything ties with T) is redone by
+// The whole cloud sits in shared memory as (x, y, z, -xx).
+//   pass 1  one query per thread, every lane of a warp reads the same candidate (broadcast LDS.128): no shuffles,
+//           no ballots, no divergence. Only the maximum score of each of <= 128 contiguous "fine" candidate
+//           groups is kept (one float per group, in shared memory). Four warps share a group of 32 queries and
+//           scan a quarter of the candidates each, so that small batches still fill the chip.
+//   thresh  the fine maxima are folded into 32 coarse group maxima; their k-th largest value T (a 32-input
+//           bitonic network in the thread's registers) is a lower bound of the k-th largest score, because k
+//           different candidates reach it. About 31 candidates reach T for k = 20, N = 1024.
+//   final   a warp per query: it lists the fine groups whose maximum reaches T (ballot), re-scores only their
+//           candidates (about a fifth of the cloud), compacts the ones with pd >= T into <= 64 keys of
+//           (order-preserving pd bits, ~index), sorts them with a bitonic network and writes the first k indices.
+//           Two queries are processed together so that their shuffle chains overlap.
+// A query with more than 64 candidates >= T (heavily duplicated points: everything ties with T) is redone by
 // its warp with a streaming sort-and-merge over all N candidates, so the result is exact for any input.
-// pd is computed by the same instruction sequence everywhere (see the file header), so the three stages agree
-// bit for bit. Padded candidates carry NaN in .w: their pd is NaN, max.f32 ignores it and `>=` rejects it.
+// pd is computed by the same instruction sequence everywhere (see the file header), so the stages agree bit for
+// bit. Padded candidates carry NaN in .w: their pd is NaN, max.f32 ignores it and `>=` rejects it.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSelGroups = 32;                 // candidate groups (>= k)
-constexpr int kSelCap = 64;                    // list slots per query
-constexpr int kSelGuard = 8;                   // candidates between two overflow checks
-constexpr int kSelListStride = kSelCap + 2;    // u16 elements per row of the per-query lists (conflict-free both ways)
-constexpr int kSelMaxN = 8192;                 // the cloud must fit shared memory as float4
+constexpr int kSelS = 4;                        // warps that share 32 queries in pass 1
+constexpr int kSelThreads = 256;
+constexpr int kSelQ = kSelThreads / kSelS;      // queries per CTA
+constexpr int kSelWarps = kSelThreads / 32;
+constexpr int kSelGroups = 32;                  // coarse groups (>= k)
+constexpr int kSelFine = 128;                   // most fine groups per cloud
+constexpr int kSelFmStride = kSelFine + 1;      // floats per query row of the fine maxima (conflict-free both ways)
+constexpr int kSelCap = 64;                     // candidate keys per query
+constexpr int kSelMaxN = 8192;                  // the cloud must fit shared memory as float4
+static_assert(kSelWarps * 2 * kSelCap * sizeof(unsigned long long) >= kSelGroups * kSelQ * sizeof(float), "key scratch holds the sorted group maxima");
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
@@ -618,9 +625,7 @@ __device__ __forceinline__ float knn_pd3(const float4 q, const float xxi, const 
     return __fsub_rn(__fmaf_rn(2.0f, dot, c.w), xxi);
 }
 
-__device__ __forceinline__ u64 knn_key3(const float4 q, const float xxi, const float4 c, int j) {
-    return ((u64)f32_to_ord(knn_pd3(q, xxi, c)) << 32) | (u64)(0xffffffffu - (unsigned)j);
-}
+__device__ __forceinline__ u64 knn_key_of(float pd, int j) { return ((u64)f32_to_ord(pd) << 32) | (u64)(0xffffffffu - (unsigned)j); }
 
 // sorts two independent key sets at once (the two shuffle chains overlap: the stage is latency-bound otherwise)
 __device__ __forceinline__ void warp_sort_desc2(u64& a, u64& b, int lane) {
@@ -643,47 +648,41 @@ __device__ __forceinline__ void warp_merge_desc2(u64& a, u64& b, int lane) {
     }
 }
 
-// S = threads (in S different warps) that share one query: each scans 1/S of the candidates in both passes
-struct KnnSelSmem {
-    size_t tile, gm, thr, buf, list, cntp, cnt, total;
+struct KnnSelPlan {
+    int fsh;     // log2(candidates per fine group), >= 3
+    int nfine;   // fine groups (<= kSelFine), all holding at least one real candidate
+    int npad;    // nfine << fsh
+    size_t smem;
 };
-static KnnSelSmem knn_select_layout(int N, int threads, int S) {
-    const int gs = cdiv(N, kSelGroups), Q = threads / S;
-    KnnSelSmem L;
-    size_t off = 0;
-    L.tile = off; off += (size_t)gs * kSelGroups * sizeof(float4);
-    L.gm = off;   off += (size_t)kSelGroups * Q * sizeof(float);
-    L.thr = off;  off += (size_t)Q * sizeof(float);
-    L.cntp = off; off += (size_t)threads * sizeof(int);
-    L.cnt = off;  off += (size_t)Q * sizeof(int);
-    L.buf = off;  off += (size_t)kSelCap * threads * sizeof(unsigned short);
-    L.list = off; off += (size_t)Q * kSelListStride * sizeof(unsigned short);
-    L.total = align_up(off, 16);
-    return L;
+static KnnSelPlan knn_select_plan(int N) {
+    KnnSelPlan p;
+    p.fsh = 3;
+    while (((long long)kSelFine << p.fsh) < N) ++p.fsh;
+    p.nfine = (N + (1 << p.fsh) - 1) >> p.fsh;
+    p.npad = p.nfine << p.fsh;
+    p.smem = (size_t)p.npad * sizeof(float4) + (size_t)kSelQ * kSelFmStride * sizeof(float) + (size_t)kSelQ * sizeof(float) +
+             (size_t)kSelWarps * 2 * kSelCap * sizeof(u64) + (size_t)kSelWarps * 2 * kSelFine;
+    return p;
 }
 
-template <int S>
-__global__ void __launch_bounds__(256)
-knn_select_kernel(const float* __restrict__ x, int N, int k, int gs, int64_t* __restrict__ idx, const KnnSelSmem L) {
+__global__ void __launch_bounds__(kSelThreads)
+knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh, int64_t* __restrict__ idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = blockDim.x, Q = T / S;
-    const int npad = gs * kSelGroups;
-    float4* sTile = reinterpret_cast<float4*>(smem_raw + L.tile);                  // [npad] (x, y, z, -xx)
-    float* sGm = reinterpret_cast<float*>(smem_raw + L.gm);                        // [32][Q] group maxima
-    float* sThr = reinterpret_cast<float*>(smem_raw + L.thr);                      // [Q]
-    int* sCntP = reinterpret_cast<int*>(smem_raw + L.cntp);                        // [T] pass-2 count of each thread, -1 = overflow
-    int* sCnt = reinterpret_cast<int*>(smem_raw + L.cnt);                          // [Q] list length, -1 = overflow
-    unsigned short* sBuf = reinterpret_cast<unsigned short*>(smem_raw + L.buf);    // [cap][T] pass-2 columns
-    unsigned short* sList = reinterpret_cast<unsigned short*>(smem_raw + L.list);  // [Q][stride] one row per query
+    const int npad = nfine << fsh;
+    float4* sTile = reinterpret_cast<float4*>(smem_raw);                            // [npad] (x, y, z, -xx)
+    float* sFm = reinterpret_cast<float*>(sTile + npad);                            // [Q][129] fine group maxima
+    float* sThr = sFm + kSelQ * kSelFmStride;                                       // [Q]
+    u64* sKey = reinterpret_cast<u64*>(sThr + kSelQ);                               // [warps][2][cap] candidate keys
+    unsigned char* sFG = reinterpret_cast<unsigned char*>(sKey + kSelWarps * 2 * kSelCap);  // [warps][2][128] fine groups to re-score
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int wq = w / S, part = w - wq * S;  // the S warps wq*S .. wq*S+S-1 share 32 queries
-    const int ql = wq * 32 + lane;            // query of this thread inside the CTA
+    const int wq = w / kSelS, part = w - wq * kSelS;  // warps wq*4 .. wq*4+3 share 32 queries
+    const int ql = wq * 32 + lane;                    // query of this thread inside the CTA
     const int b = blockIdx.y;
     const float* __restrict__ xb = x + (size_t)b * 3 * N;
 
     // the cloud and its squared norms (xx = rn(rn(x0^2 + x1^2) + x2^2), model.py:15)
-    for (int j = tid; j < npad; j += T) {
+    for (int j = tid; j < npad; j += kSelThreads) {
         float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));
         if (j < N) {
             v.x = __ldg(xb + j);
@@ -695,36 +694,44 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int gs, int64_t* __
     }
     __syncthreads();
 
-    const int i = blockIdx.x * Q + ql;
-    const float4 q = sTile[min(i, N - 1)];  // rows past N are clamped: computed, never written
-    const float xxi = -q.w;
-    constexpr int kGroupsPerPart = kSelGroups / S;
-
-    // ---- pass 1: group maxima of this thread's share of the candidates ----
+    // ---- pass 1: maxima of this warp's quarter of the fine groups, one query per thread ----
+    {
+        const int i = blockIdx.x * kSelQ + ql;
+        const float4 q = sTile[min(i, N - 1)];  // rows past N are clamped: computed, never used
+        const float xxi = -q.w;
+        const int f0 = (part * nfine) / kSelS, f1 = ((part + 1) * nfine) / kSelS;
+        const int octs = 1 << (fsh - 3);
+        float* fm = sFm + ql * kSelFmStride;
 #pragma unroll 1
-    for (int g = part * kGroupsPerPart; g < (part + 1) * kGroupsPerPart; ++g) {
-        const float4* tp = sTile + g * gs;
-        float a0 = -CUDART_INF_F, a1 = -CUDART_INF_F, a2 = -CUDART_INF_F, a3 = -CUDART_INF_F;
-        int jj = 0;
-        for (; jj + 8 <= gs; jj += 8) {
-            float p[8];
+        for (int f = f0; f < f1; ++f) {
+            const float4* tp = sTile + (f << fsh);
+            float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+#pragma unroll 1
+            for (int o = 0; o < octs; ++o, tp += 8) {
+                float p[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) p[u] = knn_pd3(q, xxi, tp[jj + u]);
-            a0 = max3(a0, p[0], p[1]);
-            a1 = max3(a1, p[2], p[3]);
-            a2 = max3(a2, p[4], p[5]);
-            a3 = max3(a3, p[6], p[7]);
+                for (int u = 0; u < 8; ++u) p[u] = knn_pd3(q, xxi, tp[u]);
+                m0 = max3(max3(m0, p[0], p[1]), p[2], p[3]);
+                m1 = max3(max3(m1, p[4], p[5]), p[6], p[7]);
+            }
+            fm[f] = max3(m0, m0, m1);
         }
-        for (; jj < gs; ++jj) a0 = max3(a0, a0, knn_pd3(q, xxi, tp[jj]));
-        sGm[g * Q + ql] = max3(max3(a0, a0, a1), a2, a3);
     }
-    if (S > 1) __syncthreads();
+    __syncthreads();
 
-    // ---- threshold: k-th largest group maximum (bitonic network over the query's 32 values) ----
+    // ---- threshold: k-th largest of the 32 coarse group maxima (bitonic network in registers) ----
     if (part == 0) {
+        const float* fm = sFm + ql * kSelFmStride;
         float v[kSelGroups];
 #pragma unroll
-        for (int g = 0; g < kSelGroups; ++g) v[g] = sGm[g * Q + ql];
+        for (int c = 0; c < kSelGroups; ++c) {
+            const int fb = (c * nfine) / kSelGroups, fe = ((c + 1) * nfine) / kSelGroups;  // at most 4 fine groups
+            float m = -CUDART_INF_F;
+#pragma unroll
+            for (int r = 0; r < kSelFine / kSelGroups; ++r)
+                if (fb + r < fe) m = fmaxf(m, fm[fb + r]);
+            v[c] = m;
+        }
 #pragma unroll
         for (int s = 2; s <= kSelGroups; s <<= 1) {
 #pragma unroll
@@ -741,102 +748,78 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int gs, int64_t* __
                 }
             }
         }
+        // v[k-1] without dynamic register indexing: through shared memory (the key scratch is idle until the barrier)
+        float* scr = reinterpret_cast<float*>(sKey);  // [32][Q] floats = exactly the key scratch
 #pragma unroll
-        for (int g = 0; g < kSelGroups; ++g) sGm[g * Q + ql] = v[g];
-        sThr[ql] = sGm[(k - 1) * Q + ql];
+        for (int c = 0; c < kSelGroups; ++c) scr[c * kSelQ + ql] = v[c];
+        sThr[ql] = scr[(k - 1) * kSelQ + ql];
     }
-    if (S > 1) __syncthreads();
-    const float thr = sThr[ql];
+    __syncthreads();
 
-    // ---- pass 2: indices of this share's candidates with pd >= thr, into this thread's column of sBuf ----
-    // (inline PTX: an unconditional 16-bit store at the cursor and a predicated cursor bump -- no select, no branch)
-    {
-        const unsigned col = static_cast<unsigned>(__cvta_generic_to_shared(sBuf + tid));
-        const unsigned stepb = 2u * T;
-        const unsigned limit = col + (kSelCap - kSelGuard) * stepb;
-        unsigned p = col;
-        bool ovf = false;
-        const int jbeg = part * kGroupsPerPart * gs, jend = jbeg + kGroupsPerPart * gs;  // a multiple of 8 candidates
+    // ---- final: a warp per query, two queries at a time ----
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int cmask = (1 << fsh) - 1;
+    u64* myKey = sKey + (size_t)w * 2 * kSelCap;
+    unsigned char* myFG = sFG + (size_t)w * 2 * kSelFine;
 #pragma unroll 1
-        for (int j = jbeg; j < jend; j += kSelGuard) {
-#pragma unroll
-            for (int u = 0; u < kSelGuard; ++u) {
-                const float pd = knn_pd3(q, xxi, sTile[j + u]);
-                const unsigned short jv = (unsigned short)(j + u);
-                asm volatile(
-                    "{\n\t.reg .pred pp;\n\t"
-                    "st.shared.u16 [%0], %1;\n\t"
-                    "setp.ge.f32 pp, %2, %3;\n\t"
-                    "@pp add.u32 %0, %0, %4;\n\t}"
-                    : "+r"(p)
-                    : "h"(jv), "f"(pd), "f"(thr), "r"(stepb)
-                    : "memory");
-            }
-            if (p > limit) {
-                ovf = true;
-                p = limit;
-            }
-        }
-        sCntP[tid] = ovf ? -1 : (int)((p - col) / stepb);
-    }
-    if (S > 1) __syncthreads(); else __syncwarp();
-
-    // ---- the S shares of a query, concatenated into its row of sList ----
-    {
-        int before = 0, total = 0;
-        bool ovf = false;
-#pragma unroll
-        for (int pp = 0; pp < S; ++pp) {
-            const int c = sCntP[(wq * S + pp) * 32 + lane];
-            ovf |= c < 0;
-            if (pp < part) before += c;
-            total += c;
-        }
-        ovf |= total > kSelCap;
-        if (!ovf) {
-            const int mine = sCntP[tid];
-            for (int e = 0; e < mine; ++e) sList[ql * kSelListStride + before + e] = sBuf[e * T + tid];
-        }
-        if (part == 0) sCnt[ql] = ovf ? -1 : total;
-    }
-    if (S > 1) __syncthreads(); else __syncwarp();
-
-    // ---- final: the warp sorts the lists of its queries, two at a time, and writes the first k indices ----
-    constexpr int kPerWarp = 32 / S;  // queries of the group this warp finishes: part, part + S, ...
-#pragma unroll 1
-    for (int n = 0; n < kPerWarp; n += 2) {
-        int tq[2], iq[2], c[2];
+    for (int n = 0; n < 32 / kSelS; n += 2) {
+        int tq[2], iq[2], ng[2], cnt[2];
+        float thr[2];
         float4 qp[2];
-        u64 key[2];
 #pragma unroll
         for (int z = 0; z < 2; ++z) {
-            tq[z] = wq * 32 + part + (n + z) * S;
-            iq[z] = blockIdx.x * Q + tq[z];
-            const bool live = (n + z) < kPerWarp && iq[z] < N;
-            c[z] = live ? sCnt[tq[z]] : 0;
-            qp[z] = sTile[min(iq[z], N - 1)];
-            key[z] = 0ull;
-            if (!live) iq[z] = -1;
+            tq[z] = wq * 32 + part + (n + z) * kSelS;
+            iq[z] = blockIdx.x * kSelQ + tq[z];
+            if (iq[z] >= N) iq[z] = -1;  // warp-uniform
+            qp[z] = sTile[max(iq[z], 0)];
+            thr[z] = sThr[tq[z]];
+            ng[z] = 0;
+            cnt[z] = 0;
         }
-        const int rounds = max((max(c[0], c[1]) + 31) >> 5, 0);
+        __syncwarp();  // the previous pair's scratch is no longer read
+        // fine groups whose maximum reaches the threshold
 #pragma unroll 1
-        for (int h = 0; h < rounds; ++h) {
-            const int e = h * 32 + lane;
-            u64 kb[2];
+        for (int f = lane; f < kSelFine; f += 32) {
 #pragma unroll
             for (int z = 0; z < 2; ++z) {
-                kb[z] = 0ull;
-                if (e < c[z]) {
-                    const int j = sList[tq[z] * kSelListStride + e];
-                    kb[z] = knn_key3(qp[z], -qp[z].w, sTile[j], j);
-                }
+                const bool qual = iq[z] >= 0 && f < nfine && sFm[tq[z] * kSelFmStride + f] >= thr[z];
+                const unsigned m = __ballot_sync(0xffffffffu, qual);
+                if (qual) myFG[z * kSelFine + ng[z] + __popc(m & lt_mask)] = (unsigned char)f;
+                ng[z] += __popc(m);
             }
-            warp_sort_desc2(kb[0], kb[1], lane);
+        }
+        __syncwarp();
+        // re-score their candidates, keep the keys of those with pd >= threshold
+        const int tot0 = ng[0] << fsh, tot1 = ng[1] << fsh;
+#pragma unroll 1
+        for (int c0 = 0; c0 < max(tot0, tot1); c0 += 32) {
+            const int c = c0 + lane;
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const bool in = c < (z == 0 ? tot0 : tot1);
+                const int j = in ? ((int)myFG[z * kSelFine + (c >> fsh)] << fsh) + (c & cmask) : 0;
+                const float pd = knn_pd3(qp[z], -qp[z].w, sTile[j]);
+                const bool pass = in && pd >= thr[z];
+                const unsigned m = __ballot_sync(0xffffffffu, pass);
+                const int pos = cnt[z] + __popc(m & lt_mask);
+                if (pass && pos < kSelCap) myKey[z * kSelCap + pos] = knn_key_of(pd, j);
+                cnt[z] += __popc(m);
+            }
+        }
+        __syncwarp();
+        // sort (<= 64 keys per query: one or two rounds of 32)
+        u64 key[2] = {0ull, 0ull};
+        const int c0n = cnt[0] <= kSelCap ? cnt[0] : 0, c1n = cnt[1] <= kSelCap ? cnt[1] : 0;
+#pragma unroll 1
+        for (int h = 0; h * 32 < max(c0n, c1n); ++h) {
+            const int e = h * 32 + lane;
+            u64 ka = e < c0n ? myKey[e] : 0ull, kb = e < c1n ? myKey[kSelCap + e] : 0ull;
+            warp_sort_desc2(ka, kb, lane);
             if (h == 0) {
-                key[0] = kb[0];
-                key[1] = kb[1];
+                key[0] = ka;
+                key[1] = kb;
             } else {
-                const u64 r0 = __shfl_sync(0xffffffffu, kb[0], 31 - lane), r1 = __shfl_sync(0xffffffffu, kb[1], 31 - lane);
+                const u64 r0 = __shfl_sync(0xffffffffu, ka, 31 - lane), r1 = __shfl_sync(0xffffffffu, kb, 31 - lane);
                 key[0] = key[0] > r0 ? key[0] : r0;
                 key[1] = key[1] > r1 ? key[1] : r1;
                 warp_merge_desc2(key[0], key[1], lane);
@@ -845,12 +828,12 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int gs, int64_t* __
 #pragma unroll
         for (int z = 0; z < 2; ++z) {
             if (iq[z] < 0) continue;  // warp-uniform
-            if (c[z] < 0) {
-                // overflow: streaming sort-and-merge over the whole cloud
+            if (cnt[z] > kSelCap) {
+                // more than 64 candidates tie with the threshold: streaming sort-and-merge over the whole cloud
                 u64 kk = 0ull, tau = 0ull;
                 for (int j0 = 0; j0 < N; j0 += 32) {
                     const int j = j0 + lane;
-                    u64 kb = j < N ? knn_key3(qp[z], -qp[z].w, sTile[j], j) : 0ull;
+                    u64 kb = j < N ? knn_key_of(knn_pd3(qp[z], -qp[z].w, sTile[j]), j) : 0ull;
                     if (!(kb > tau)) kb = 0ull;
                     if (__any_sync(0xffffffffu, kb != 0ull)) {
                         kb = warp_sort_desc(kb, lane);
@@ -971,19 +954,10 @@ int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx,
     if ((size_t)C * 32 * sizeof(float) > 160 * 1024) return fail(FPSG_EINVAL, "knn: C=%d too large", C);
     const KnnPlan p = make_knn_plan(B, C, N, k);
     if (!ws || ws_bytes < p.ws_bytes) return fail(FPSG_EWORKSPACE, "knn: workspace of %zu bytes required, %zu given", p.ws_bytes, ws ? ws_bytes : (size_t)0);
-    if (C == 3 && k <= 32 && N <= kSelMaxN && !getenv("FPSG_KNN_BULK")) {  // two-pass selection kernel (needs no workspace)
-        // S warps share 32 queries so that even a small batch fills the chip: aim at >= 4 warps per SM sub-partition
-        const long long qwarps = (long long)B * cdiv(N, 32);
-        int S = qwarps >= 4LL * 4 * sm_count_knn() ? 1 : (qwarps * 2 >= 4LL * 4 * sm_count_knn() ? 2 : 4);
-        if (const char* e = getenv("FPSG_KNN_SPLIT")) {  // tuning override: 1, 2 or 4
-            const int v = atoi(e);
-            if (v == 1 || v == 2 || v == 4) S = v;
-        }
-        const int threads = 256;
-        const KnnSelSmem L = knn_select_layout(N, threads, S);
-        auto kern = S == 1 ? knn_select_kernel<1> : (S == 2 ? knn_select_kernel<2> : knn_select_kernel<4>);
-        if (L.total > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        kern<<<dim3((unsigned)cdiv(N, threads / S), (unsigned)B), threads, L.total, stream>>>(x, N, k, cdiv(N, kSelGroups), idx, L);
+    if (C == 3 && k <= 32 && N <= kSelMaxN && !getenv("FPSG_KNN_BULK")) {  // threshold-selection kernel (needs no workspace)
+        const KnnSelPlan sp = knn_select_plan(N);
+        if (sp.smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
+        knn_select_kernel<<<dim3((unsigned)cdiv(N, kSelQ), (unsigned)B), kSelThreads, sp.smem, stream>>>(x, N, k, sp.nfine, sp.fsh, idx);
         FPSG_CUDA_OK(cudaGetLastError());
         return FPSG_OK;
     }
