@@ -608,6 +608,7 @@ constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kSelGroups = 32;                  // coarse groups (>= k)
 constexpr int kSelFine = 128;                   // most fine groups per cloud
 constexpr int kSelFmStride = kSelFine + 1;      // floats per query row of the fine maxima (conflict-free both ways)
+constexpr int kSelFgStride = kSelFine + 4;      // bytes per list of fine groups to re-score (+ the sentinel)
 constexpr int kSelCap = 64;                     // candidate keys per query
 constexpr int kSelMaxN = 8192;                  // the cloud must fit shared memory as float4
 static_assert(kSelWarps * 2 * kSelCap * sizeof(unsigned long long) >= kSelGroups * kSelQ * sizeof(float), "key scratch holds the sorted group maxima");
@@ -660,8 +661,8 @@ static KnnSelPlan knn_select_plan(int N) {
     while (((long long)kSelFine << p.fsh) < N) ++p.fsh;
     p.nfine = (N + (1 << p.fsh) - 1) >> p.fsh;
     p.npad = p.nfine << p.fsh;
-    p.smem = (size_t)p.npad * sizeof(float4) + (size_t)kSelQ * kSelFmStride * sizeof(float) + (size_t)kSelQ * sizeof(float) +
-             (size_t)kSelWarps * 2 * kSelCap * sizeof(u64) + (size_t)kSelWarps * 2 * kSelFine;
+    p.smem = (size_t)(p.npad + (1 << p.fsh)) * sizeof(float4) + (size_t)kSelQ * kSelFmStride * sizeof(float) + (size_t)kSelQ * sizeof(float) +
+             (size_t)kSelWarps * 2 * kSelCap * sizeof(u64) + (size_t)kSelWarps * 2 * kSelFgStride;
     return p;
 }
 
@@ -669,8 +670,9 @@ __global__ void __launch_bounds__(kSelThreads)
 knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh, int64_t* __restrict__ idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int npad = nfine << fsh;
-    float4* sTile = reinterpret_cast<float4*>(smem_raw);                            // [npad] (x, y, z, -xx)
-    float* sFm = reinterpret_cast<float*>(sTile + npad);                            // [Q][129] fine group maxima
+    const int ntile = npad + (1 << fsh);  // one more fine group, all padding: the target of out-of-range lanes
+    float4* sTile = reinterpret_cast<float4*>(smem_raw);                            // [ntile] (x, y, z, -xx)
+    float* sFm = reinterpret_cast<float*>(sTile + ntile);                           // [Q][129] fine group maxima
     float* sThr = sFm + kSelQ * kSelFmStride;                                       // [Q]
     u64* sKey = reinterpret_cast<u64*>(sThr + kSelQ);                               // [warps][2][cap] candidate keys
     unsigned char* sFG = reinterpret_cast<unsigned char*>(sKey + kSelWarps * 2 * kSelCap);  // [warps][2][128] fine groups to re-score
@@ -682,7 +684,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     const float* __restrict__ xb = x + (size_t)b * 3 * N;
 
     // the cloud and its squared norms (xx = rn(rn(x0^2 + x1^2) + x2^2), model.py:15)
-    for (int j = tid; j < npad; j += kSelThreads) {
+    for (int j = tid; j < ntile; j += kSelThreads) {
         float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));
         if (j < N) {
             v.x = __ldg(xb + j);
@@ -702,19 +704,30 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
         const int f0 = (part * nfine) / kSelS, f1 = ((part + 1) * nfine) / kSelS;
         const int octs = 1 << (fsh - 3);
         float* fm = sFm + ql * kSelFmStride;
-#pragma unroll 1
-        for (int f = f0; f < f1; ++f) {
-            const float4* tp = sTile + (f << fsh);
-            float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
-#pragma unroll 1
-            for (int o = 0; o < octs; ++o, tp += 8) {
+        if (fsh == 3) {  // one octet per fine group (N <= 1024): no inner loop
+#pragma unroll 2
+            for (int f = f0; f < f1; ++f) {
+                const float4* tp = sTile + (f << 3);
                 float p[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) p[u] = knn_pd3(q, xxi, tp[u]);
-                m0 = max3(max3(m0, p[0], p[1]), p[2], p[3]);
-                m1 = max3(max3(m1, p[4], p[5]), p[6], p[7]);
+                fm[f] = max3(max3(max3(p[0], p[1], p[2]), p[3], p[4]), max3(p[5], p[6], p[7]), p[0]);
             }
-            fm[f] = max3(m0, m0, m1);
+        } else {
+#pragma unroll 1
+            for (int f = f0; f < f1; ++f) {
+                const float4* tp = sTile + (f << fsh);
+                float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+#pragma unroll 2
+                for (int o = 0; o < octs; ++o, tp += 8) {
+                    float p[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) p[u] = knn_pd3(q, xxi, tp[u]);
+                    m0 = max3(max3(m0, p[0], p[1]), p[2], p[3]);
+                    m1 = max3(max3(m1, p[4], p[5]), p[6], p[7]);
+                }
+                fm[f] = max3(m0, m0, m1);
+            }
         }
     }
     __syncthreads();
@@ -760,7 +773,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     const unsigned lt_mask = (1u << lane) - 1u;
     const int cmask = (1 << fsh) - 1;
     u64* myKey = sKey + (size_t)w * 2 * kSelCap;
-    unsigned char* myFG = sFG + (size_t)w * 2 * kSelFine;
+    unsigned char* myFG = sFG + (size_t)w * 2 * kSelFgStride;
 #pragma unroll 1
     for (int n = 0; n < 32 / kSelS; n += 2) {
         int tq[2], iq[2], ng[2], cnt[2];
@@ -784,10 +797,11 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
             for (int z = 0; z < 2; ++z) {
                 const bool qual = iq[z] >= 0 && f < nfine && sFm[tq[z] * kSelFmStride + f] >= thr[z];
                 const unsigned m = __ballot_sync(0xffffffffu, qual);
-                if (qual) myFG[z * kSelFine + ng[z] + __popc(m & lt_mask)] = (unsigned char)f;
+                if (qual) myFG[z * kSelFgStride + ng[z] + __popc(m & lt_mask)] = (unsigned char)f;
                 ng[z] += __popc(m);
             }
         }
+        if (lane < 2) myFG[lane * kSelFgStride + ng[lane]] = (unsigned char)nfine;  // sentinel: the all-padding group
         __syncwarp();
         // re-score their candidates, keep the keys of those with pd >= threshold
         const int tot0 = ng[0] << fsh, tot1 = ng[1] << fsh;
@@ -796,10 +810,9 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
             const int c = c0 + lane;
 #pragma unroll
             for (int z = 0; z < 2; ++z) {
-                const bool in = c < (z == 0 ? tot0 : tot1);
-                const int j = in ? ((int)myFG[z * kSelFine + (c >> fsh)] << fsh) + (c & cmask) : 0;
+                const int j = ((int)myFG[z * kSelFgStride + min(c >> fsh, ng[z])] << fsh) + (c & cmask);  // past the list: padding
                 const float pd = knn_pd3(qp[z], -qp[z].w, sTile[j]);
-                const bool pass = in && pd >= thr[z];
+                const bool pass = pd >= thr[z];
                 const unsigned m = __ballot_sync(0xffffffffu, pass);
                 const int pos = cnt[z] + __popc(m & lt_mask);
                 if (pass && pos < kSelCap) myKey[z * kSelCap + pos] = knn_key_of(pd, j);
