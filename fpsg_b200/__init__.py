@@ -4,9 +4,9 @@ forward/backward and the DGCNN kNN graph, behind the reference's own call surfac
     from fpsg_b200 import chamfer_distance, chamfer_loss, sided_distance, knn
     import fpsg_b200.shims; fpsg_b200.shims.install()   # makes the reference source run unchanged
 """
-from .chamfer import chamfer_distance, chamfer_loss, sided_distance
+from .chamfer import chamfer_distance, chamfer_loss, chamfer_loss_multi, sided_distance
 from .graph_feature import get_graph_feature
 from .knn import knn
 
-__all__ = ["chamfer_distance", "chamfer_loss", "sided_distance", "knn", "get_graph_feature"]
+__all__ = ["chamfer_distance", "chamfer_loss", "chamfer_loss_multi", "sided_distance", "knn", "get_graph_feature"]
 __version__ = "0.1.0"

@@ -18,8 +18,17 @@ _i64p = ctypes.c_void_p
 _lib = None
 
 
+MAX_SEGMENTS = 8
+
+
 class FpsgError(RuntimeError):
     pass
+
+
+class ChamferSegment(ctypes.Structure):
+    """``fpsg_chamfer_segment_t`` of include/fpsg_b200.h."""
+    _fields_ = [("p1", ctypes.c_void_p), ("p2", ctypes.c_void_p), ("gp1", ctypes.c_void_p), ("gp2", ctypes.c_void_p),
+                ("batch", ctypes.c_int), ("weight", ctypes.c_float)]
 
 
 def _declare(L: ctypes.CDLL) -> None:
@@ -40,6 +49,11 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_chamfer_loss_fwd.argtypes = [vp, vp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, vp, c_size_t, vp]
     L.fpsg_chamfer_loss_bwd.restype = c_int
     L.fpsg_chamfer_loss_bwd.argtypes = [vp, vp, vp, vp, vp, c_float, c_float, c_int, c_int, c_int, vp, vp, vp, c_size_t, vp]
+    segp = ctypes.POINTER(ChamferSegment)
+    L.fpsg_chamfer_multi_loss_fwd.restype = c_int
+    L.fpsg_chamfer_multi_loss_fwd.argtypes = [segp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, c_size_t, vp]
+    L.fpsg_chamfer_multi_loss_bwd.restype = c_int
+    L.fpsg_chamfer_multi_loss_bwd.argtypes = [segp, c_int, vp, vp, vp, c_float, c_float, c_int, c_int, vp]
     L.fpsg_knn_workspace_bytes.restype = c_size_t
     L.fpsg_knn_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     L.fpsg_knn_fwd.restype = c_int

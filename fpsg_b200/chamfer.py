@@ -7,6 +7,8 @@ Three public call surfaces, all ``torch.autograd`` aware:
 * ``chamfer_loss(p1, p2, w1=1., w2=1.) -> (B,)``               -- what Kaolin's ``chamfer_distance`` returns
   (``w1*mean(dist1) + w2*mean(dist2)``, squared L2); fused forward reduction and uniform-gradient backward.
 * ``sided_distance(p1, p2) -> (dist, idx)``                    -- Kaolin's one-directional primitive.
+* ``chamfer_loss_multi(pairs, weights) -> (total, sums, loss)`` -- several calls (the query-set and support-set
+  losses of one training step, src/models/few_shot.py:109-122) and their weighted sum in one launch chain.
 
 Error behaviour follows Kaolin's TORCH_CHECKs: anything but CUDA float32 tensors of shape (B,N,3)/(B,M,3) raises;
 non-contiguous inputs are made contiguous. There is no CPU path.
@@ -188,6 +190,86 @@ class _ChamferLoss(torch.autograd.Function):
                                              None, 0, _stream_ptr(dev))
                 _lib.check(rc)
         return gp1, gp2, None, None
+
+
+class _ChamferLossMulti(torch.autograd.Function):
+    """forward(w1, w2, weights, p1_0, p2_0, p1_1, p2_1, ...) -> (total (), sums (nseg,), loss (Btot,))"""
+
+    @staticmethod
+    def forward(ctx, w1, w2, weights, *clouds):
+        nseg = len(clouds) // 2
+        pairs = [_check_clouds(clouds[2 * s], clouds[2 * s + 1]) for s in range(nseg)]
+        N, M = pairs[0][0].shape[1], pairs[0][1].shape[1]
+        dev = pairs[0][0].device
+        for a, b in pairs:
+            if a.shape[1] != N or b.shape[1] != M:
+                raise RuntimeError(f"all segments must share N and M: got {(a.shape[1], b.shape[1])} vs {(N, M)}")
+            if a.device != dev:
+                raise RuntimeError("all segments must live on the same device")
+        Btot = sum(a.shape[0] for a, _ in pairs)
+        L = _lib.lib()
+        segs = (_lib.ChamferSegment * nseg)()
+        for s, (a, b) in enumerate(pairs):
+            segs[s].p1, segs[s].p2, segs[s].gp1, segs[s].gp2 = a.data_ptr(), b.data_ptr(), None, None
+            segs[s].batch, segs[s].weight = a.shape[0], float(weights[s])
+        idx = torch.empty((Btot * (N + M),), dtype=torch.int64, device=dev)
+        out = torch.empty((1 + nseg + Btot,), dtype=torch.float32, device=dev)  # totals, then the per-pair losses
+        with _device_guard(dev):
+            ws, nbytes = _workspace(Btot, N, M, dev) if Btot > 0 else (None, 0)
+            _lib.check(L.fpsg_chamfer_multi_loss_fwd(segs, nseg, N, M, float(w1), float(w2), out[1 + nseg:].data_ptr(),
+                                                     out.data_ptr(), idx.data_ptr(), idx[Btot * N:].data_ptr(),
+                                                     ws.data_ptr() if ws is not None else None, nbytes, _stream_ptr(dev)))
+        ctx.save_for_backward(idx, *[t for pr in pairs for t in pr])
+        ctx.meta = (float(w1), float(w2), tuple(float(w) for w in weights), N, M, Btot)
+        total, sums, loss = out[0], out[1:1 + nseg], out[1 + nseg:]
+        ctx.mark_non_differentiable(sums, loss)
+        return total, sums, loss
+
+    @staticmethod
+    def backward(ctx, gtotal, _gsums, _gloss):
+        idx, *clouds = ctx.saved_tensors
+        w1, w2, weights, N, M, Btot = ctx.meta
+        nseg = len(clouds) // 2
+        dev = idx.device
+        L = _lib.lib()
+        segs = (_lib.ChamferSegment * nseg)()
+        grads = [None] * (2 * nseg)
+        for s in range(nseg):
+            a, b = clouds[2 * s], clouds[2 * s + 1]
+            if ctx.needs_input_grad[3 + 2 * s]:
+                grads[2 * s] = torch.empty_like(a)
+            if ctx.needs_input_grad[4 + 2 * s]:
+                grads[2 * s + 1] = torch.empty_like(b)
+            segs[s].p1, segs[s].p2 = a.data_ptr(), b.data_ptr()
+            segs[s].gp1 = grads[2 * s].data_ptr() if grads[2 * s] is not None else None
+            segs[s].gp2 = grads[2 * s + 1].data_ptr() if grads[2 * s + 1] is not None else None
+            segs[s].batch, segs[s].weight = a.shape[0], weights[s]
+        if Btot > 0 and any(g is not None for g in grads):
+            gtotal = gtotal.to(torch.float32).contiguous()
+            with _device_guard(dev):
+                _lib.check(L.fpsg_chamfer_multi_loss_bwd(segs, nseg, idx.data_ptr(), idx[Btot * N:].data_ptr(), gtotal.data_ptr(),
+                                                         w1, w2, N, M, _stream_ptr(dev)))
+        return (None, None, None, *grads)
+
+
+def chamfer_loss_multi(pairs, weights=None, w1: float = 1.0, w2: float = 1.0):
+    """Several Chamfer loss calls and the reduction the reference applies on top, in one launch chain.
+
+    ``pairs`` = [(p1_0, p2_0), (p1_1, p2_1), ...] (each as for ``chamfer_loss``; all with the same N and M),
+    ``weights`` = one factor per pair of tensors (default 1). Returns ``(total, sums, loss)``:
+    ``sums[s] = chamfer_loss(p1_s, p2_s).sum()``, ``total = sum_s weights[s] * sums[s]`` (differentiable w.r.t. the
+    clouds; ``sums`` and the per-pair ``loss`` (Btot,) are for logging and carry no gradient).
+
+    This is src/models/few_shot.py:109-122 -- ``loss_rec_q = pc_metric(syn_q, ref_q).sum()``, ``loss_rec_s = ...``,
+    ``query_factor * loss_rec_q + support_factor * loss_rec_s`` -- as one forward and one backward call."""
+    pairs = list(pairs)
+    if not 1 <= len(pairs) <= _lib.MAX_SEGMENTS:
+        raise RuntimeError(f"need 1..{_lib.MAX_SEGMENTS} pairs of clouds, got {len(pairs)}")
+    weights = [1.0] * len(pairs) if weights is None else [float(w) for w in weights]
+    if len(weights) != len(pairs):
+        raise RuntimeError("one weight per pair of clouds is required")
+    flat = [t for pr in pairs for t in pr]
+    return _ChamferLossMulti.apply(float(w1), float(w2), tuple(weights), *flat)
 
 
 def chamfer_distance(p1: torch.Tensor, p2: torch.Tensor):

@@ -18,12 +18,34 @@ int fail(int code, const char* fmt, ...) {
 
 // implemented in chamfer_fwd.cu / chamfer_bwd.cu / knn.cu
 size_t chamfer_forward_workspace(int B, int N, int M);
-int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
-                           int64_t* idx2, float* loss, float w1, float w2, void* ws, size_t ws_bytes, cudaStream_t stream,
-                           bool sweep_only);
-int chamfer_backward_launch(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2, const float* g1,
-                            const float* g2, bool uniform, float w1, float w2, int B, int N, int M, float* gp1, float* gp2,
-                            cudaStream_t stream);
+int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
+                           int64_t* idx2, float* loss, float* totals, float w1, float w2, void* ws, size_t ws_bytes,
+                           cudaStream_t stream, bool sweep_only);
+int chamfer_backward_launch(const SegTable& seg, const int64_t* idx1, const int64_t* idx2, const float* g1, const float* g2,
+                            bool uniform, const float* gtotal, float w1, float w2, int B, int N, int M, cudaStream_t stream);
+
+// host array of segments -> the table the kernels index; returns the total number of pairs or a negative error
+static int make_seg_table(const fpsg_chamfer_segment_t* segs, int nseg, SegTable* out) {
+    if (!segs || nseg < 1 || nseg > FPSG_MAX_SEGMENTS)
+        return fail(FPSG_EINVAL, "chamfer_multi: need 1..%d segments (got %d)", FPSG_MAX_SEGMENTS, nseg);
+    SegTable t = {};
+    long long total = 0;
+    for (int i = 0; i < nseg; ++i) {
+        if (segs[i].batch < 0) return fail(FPSG_EINVAL, "chamfer_multi: segment %d has batch %d", i, segs[i].batch);
+        t.p1[i] = segs[i].p1;
+        t.p2[i] = segs[i].p2;
+        t.gp1[i] = segs[i].gp1;
+        t.gp2[i] = segs[i].gp2;
+        t.b0[i] = (int)total;
+        t.weight[i] = segs[i].weight;
+        total += segs[i].batch;
+        if (total > 65535) return fail(FPSG_EINVAL, "chamfer_multi: more than 65535 pairs in one call");
+    }
+    t.b0[nseg] = (int)total;
+    t.n = nseg;
+    *out = t;
+    return (int)total;
+}
 int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out, cudaStream_t stream);
 size_t edge_feature_backward_workspace(int B, int C, int N, int k);
 int edge_feature_backward_launch(const float* g, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws, size_t ws_bytes,
@@ -72,21 +94,22 @@ size_t fpsg_chamfer_fwd_workspace_bytes(int B, int N, int M) { return chamfer_fo
 int fpsg_chamfer_fwd(const float* p1, const float* p2, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
                      int64_t* idx2, void* ws, size_t ws_bytes, fpsg_stream_t stream) {
     if (B > 0 && (!dist1 || !dist2)) return fail(FPSG_EINVAL, "chamfer_fwd: null dist1/dist2");
-    return chamfer_forward_launch(p1, p2, B, N, M, dist1, dist2, idx1, idx2, nullptr, 1.f, 1.f, ws, ws_bytes,
-                                  static_cast<cudaStream_t>(stream), false);
+    return chamfer_forward_launch(single_segment(p1, p2, nullptr, nullptr, B), B, N, M, dist1, dist2, idx1, idx2, nullptr, nullptr,
+                                  1.f, 1.f, ws, ws_bytes, static_cast<cudaStream_t>(stream), false);
 }
 
 int fpsg_chamfer_sweep_only(const float* p1, const float* p2, int B, int N, int M, void* ws, size_t ws_bytes,
                             fpsg_stream_t stream) {
-    return chamfer_forward_launch(p1, p2, B, N, M, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 1.f, ws, ws_bytes,
-                                  static_cast<cudaStream_t>(stream), true);
+    return chamfer_forward_launch(single_segment(p1, p2, nullptr, nullptr, B), B, N, M, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                  nullptr, 1.f, 1.f, ws, ws_bytes, static_cast<cudaStream_t>(stream), true);
 }
 
 size_t fpsg_chamfer_bwd_workspace_bytes(int, int, int) { return 0; }
 
 int fpsg_chamfer_bwd(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2, const float* g1,
                      const float* g2, int B, int N, int M, float* gp1, float* gp2, void*, size_t, fpsg_stream_t stream) {
-    return chamfer_backward_launch(p1, p2, idx1, idx2, g1, g2, false, 1.f, 1.f, B, N, M, gp1, gp2,
+    if (B > 0 && (gp1 || gp2) && (!p1 || !p2)) return fail(FPSG_EINVAL, "chamfer_bwd: null input pointer");
+    return chamfer_backward_launch(single_segment(p1, p2, gp1, gp2, B), idx1, idx2, g1, g2, false, nullptr, 1.f, 1.f, B, N, M,
                                    static_cast<cudaStream_t>(stream));
 }
 
@@ -94,15 +117,41 @@ int fpsg_chamfer_loss_fwd(const float* p1, const float* p2, int B, int N, int M,
                           float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, void* ws, size_t ws_bytes,
                           fpsg_stream_t stream) {
     if (B > 0 && !loss) return fail(FPSG_EINVAL, "chamfer_loss_fwd: null loss");
-    return chamfer_forward_launch(p1, p2, B, N, M, dist1, dist2, idx1, idx2, loss, w1, w2, ws, ws_bytes,
-                                  static_cast<cudaStream_t>(stream), false);
+    return chamfer_forward_launch(single_segment(p1, p2, nullptr, nullptr, B), B, N, M, dist1, dist2, idx1, idx2, loss, nullptr,
+                                  w1, w2, ws, ws_bytes, static_cast<cudaStream_t>(stream), false);
 }
 
 int fpsg_chamfer_loss_bwd(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2, const float* gloss,
                           float w1, float w2, int B, int N, int M, float* gp1, float* gp2, void*, size_t,
                           fpsg_stream_t stream) {
-    return chamfer_backward_launch(p1, p2, idx1, idx2, gloss, gloss, true, w1, w2, B, N, M, gp1, gp2,
+    if (B > 0 && (gp1 || gp2) && (!p1 || !p2)) return fail(FPSG_EINVAL, "chamfer_bwd: null input pointer");
+    return chamfer_backward_launch(single_segment(p1, p2, gp1, gp2, B), idx1, idx2, gloss, gloss, true, nullptr, w1, w2, B, N, M,
                                    static_cast<cudaStream_t>(stream));
+}
+
+int fpsg_chamfer_multi_loss_fwd(const fpsg_chamfer_segment_t* segs_host, int nseg, int N, int M, float w1, float w2,
+                                float* loss, float* totals, int64_t* idx1, int64_t* idx2, void* ws, size_t ws_bytes,
+                                fpsg_stream_t stream) {
+    SegTable t;
+    const int B = make_seg_table(segs_host, nseg, &t);
+    if (B < 0) return B;
+    if (!totals) return fail(FPSG_EINVAL, "chamfer_multi_loss_fwd: null totals");
+    if (B == 0) {  // nothing to launch: the sums are zero
+        FPSG_CUDA_OK(cudaMemsetAsync(totals, 0, sizeof(float) * (size_t)(1 + nseg), static_cast<cudaStream_t>(stream)));
+        return FPSG_OK;
+    }
+    if (!loss) return fail(FPSG_EINVAL, "chamfer_multi_loss_fwd: null loss");
+    return chamfer_forward_launch(t, B, N, M, nullptr, nullptr, idx1, idx2, loss, totals, w1, w2, ws, ws_bytes,
+                                  static_cast<cudaStream_t>(stream), false);
+}
+
+int fpsg_chamfer_multi_loss_bwd(const fpsg_chamfer_segment_t* segs_host, int nseg, const int64_t* idx1, const int64_t* idx2,
+                                const float* gtotal, float w1, float w2, int N, int M, fpsg_stream_t stream) {
+    SegTable t;
+    const int B = make_seg_table(segs_host, nseg, &t);
+    if (B < 0) return B;
+    if (!gtotal) return fail(FPSG_EINVAL, "chamfer_multi_loss_bwd: null gtotal");
+    return chamfer_backward_launch(t, idx1, idx2, nullptr, nullptr, true, gtotal, w1, w2, B, N, M, static_cast<cudaStream_t>(stream));
 }
 
 size_t fpsg_knn_workspace_bytes(int B, int C, int N, int k) { return knn_workspace(B, C, N, k); }

@@ -22,26 +22,26 @@ constexpr int kBwdThreads = 256;
 constexpr int kBwdChunk = 2048;  // arg-min indices of the other cloud scanned per CSR build
 
 struct BwdSide {
-    const float* A;        // (B,Na,3) the cloud whose gradient is produced
-    const float* Q;        // (B,Nq,3) the other cloud
+    bool first;            // A = the p1 side of the segment table (gradient to gp1), else the p2 side
     const int64_t* idxA;   // (B,Na)   nearest Q point of every A point
     const int64_t* idxQ;   // (B,Nq)   nearest A point of every Q point
     const float* gA;       // upstream gradient of distA: (B,Na), or (B,) when uniform
     const float* gQ;       // upstream gradient of distQ: (B,Nq), or (B,) when uniform
     float scaleA, scaleQ;  // uniform mode: g = (g[b] * w) / count  -> scale carries w, divisor carries count
     float divA, divQ;
-    float* out;            // (B,Na,3) or nullptr (side not requested)
     int Na, Nq;
     int blocks;            // CTAs per pair for this side
 };
 
-// uniform mode: the gradient that `.sum()` / kaolin's mean sends to every element of a pair, (gloss[b] * w) / count
-__device__ __forceinline__ float uniform_weight(const float* g, float scale, float div, size_t b) {
-    return __fdiv_rn(__fmul_rn(__ldg(g + b), scale), div);
+// uniform mode: the gradient that `.sum()` / kaolin's mean sends to every element of a pair, (gloss * w) / count
+__device__ __forceinline__ float uniform_weight(float gloss, float scale, float div) {
+    return __fdiv_rn(__fmul_rn(gloss, scale), div);
 }
 
+// seg: where the clouds and the gradient outputs live. gtotal (multi-segment loss only): device scalar, the
+// upstream gradient of the weighted total; the pairs of segment s then receive gloss = gtotal * weight_s.
 __global__ void __launch_bounds__(kBwdThreads)
-chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
+chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, const float* __restrict__ gtotal) {
     __shared__ int sCount[kBwdThreads];
     __shared__ int sCursor[kBwdThreads];
     __shared__ int sWarp[kBwdThreads / 32];
@@ -58,13 +58,22 @@ chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
     const int i = i0 + tid;
     const bool live = i < S.Na;
 
-    const float* __restrict__ Ab = S.A + (size_t)b * S.Na * 3;
-    const float* __restrict__ Qb = S.Q + (size_t)b * S.Nq * 3;
+    const int sg = seg.n == 1 ? 0 : seg_find(seg, b);
+    const int bl = b - seg.b0[sg];  // pair index inside its segment
+    float* const outb = (S.first ? seg.gp1[sg] : seg.gp2[sg]);
+    if (outb == nullptr) return;  // this segment does not want this side's gradient (CTA-uniform)
+    const float* __restrict__ Ab = (S.first ? seg.p1[sg] : seg.p2[sg]) + (size_t)bl * S.Na * 3;
+    const float* __restrict__ Qb = (S.first ? seg.p2[sg] : seg.p1[sg]) + (size_t)bl * S.Nq * 3;
     const int64_t* __restrict__ iQ = S.idxQ + (size_t)b * S.Nq;
 
     // 2*g of the two edge kinds when the upstream gradient is uniform over the pair
-    const float uA = uniform ? __fmul_rn(2.0f, uniform_weight(S.gA, S.scaleA, S.divA, b)) : 0.f;
-    const float uQ = uniform ? __fmul_rn(2.0f, uniform_weight(S.gQ, S.scaleQ, S.divQ, b)) : 0.f;
+    float uA = 0.f, uQ = 0.f;
+    if (uniform) {
+        const float glA = gtotal ? __fmul_rn(__ldg(gtotal), seg.weight[sg]) : __ldg(S.gA + b);
+        const float glQ = gtotal ? glA : __ldg(S.gQ + b);
+        uA = __fmul_rn(2.0f, uniform_weight(glA, S.scaleA, S.divA));
+        uQ = __fmul_rn(2.0f, uniform_weight(glQ, S.scaleQ, S.divQ));
+    }
 
     constexpr int kPer = kBwdChunk / kBwdThreads;  // arg-min indices of the other cloud per thread per chunk
 
@@ -163,24 +172,30 @@ chamfer_bwd_kernel(BwdSide s1, BwdSide s2, bool uniform) {
         __syncthreads();
     }
     if (live) {
-        float* o = S.out + ((size_t)b * S.Na + i) * 3;
+        float* o = outb + ((size_t)bl * S.Na + i) * 3;
         o[0] = (float)gx;
         o[1] = (float)gy;
         o[2] = (float)gz;
     }
 }
 
-int chamfer_backward_launch(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2, const float* g1,
-                            const float* g2, bool uniform, float w1, float w2, int B, int N, int M, float* gp1, float* gp2,
-                            cudaStream_t stream) {
+int chamfer_backward_launch(const SegTable& seg, const int64_t* idx1, const int64_t* idx2, const float* g1, const float* g2,
+                            bool uniform, const float* gtotal, float w1, float w2, int B, int N, int M, cudaStream_t stream) {
     if (B < 0 || N < 1 || M < 1) return fail(FPSG_EINVAL, "chamfer_bwd: need B >= 0, N >= 1, M >= 1 (got B=%d N=%d M=%d)", B, N, M);
-    if (B == 0 || (!gp1 && !gp2)) return FPSG_OK;
-    if (!p1 || !p2 || !idx1 || !idx2 || !g1 || !g2) return fail(FPSG_EINVAL, "chamfer_bwd: null input pointer");
+    bool want1 = false, want2 = false;
+    for (int sg = 0; sg < seg.n; ++sg) {
+        if (seg.b0[sg + 1] == seg.b0[sg]) continue;
+        want1 |= seg.gp1[sg] != nullptr;
+        want2 |= seg.gp2[sg] != nullptr;
+        if (!seg.p1[sg] || !seg.p2[sg]) return fail(FPSG_EINVAL, "chamfer_bwd: null input pointer");
+    }
+    if (B == 0 || (!want1 && !want2)) return FPSG_OK;
+    if (!idx1 || !idx2 || (!gtotal && (!g1 || !g2))) return fail(FPSG_EINVAL, "chamfer_bwd: null input pointer");
     if (B > 65535) return fail(FPSG_EINVAL, "chamfer_bwd: B > 65535 not supported in one call");
-    BwdSide s1{p1, p2, idx1, idx2, g1, g2, w1, w2, (float)N, (float)M, gp1, N, M, gp1 ? cdiv(N, kBwdThreads) : 0};
-    BwdSide s2{p2, p1, idx2, idx1, g2, g1, w2, w1, (float)M, (float)N, gp2, M, N, gp2 ? cdiv(M, kBwdThreads) : 0};
+    BwdSide s1{true, idx1, idx2, g1, g2, w1, w2, (float)N, (float)M, N, M, want1 ? cdiv(N, kBwdThreads) : 0};
+    BwdSide s2{false, idx2, idx1, g2, g1, w2, w1, (float)M, (float)N, M, N, want2 ? cdiv(M, kBwdThreads) : 0};
     const dim3 grid((unsigned)(s1.blocks + s2.blocks), (unsigned)B);
-    FPSG_CUDA_OK(launch_pdl(chamfer_bwd_kernel, grid, dim3(kBwdThreads), 0, stream, s1, s2, uniform));
+    FPSG_CUDA_OK(launch_pdl(chamfer_bwd_kernel, grid, dim3(kBwdThreads), 0, stream, seg, s1, s2, uniform, gtotal));
     return FPSG_OK;
 }
 

@@ -121,19 +121,18 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     p.losspart_off = off;
     off += align_up((size_t)B * (p.nrb + p.ncb) * sizeof(double), 256);
     p.counters_off = off;
-    off += align_up((size_t)B * sizeof(unsigned), 256);
+    off += align_up(((size_t)B + 1) * sizeof(unsigned), 256);
     p.total_bytes = off;
     return p;
 }
 
 struct SweepArgs {
-    const float* p1;
-    const float* p2;
+    SegTable seg;   // the clouds: p1 (B,N,3), p2 (B,M,3), possibly in several separately allocated segments
     int N, M, strips, ups, q, r, maxslots, Mpad;
     u64* rowpart;   // [B*strips][maxslots][TN]   (row partial minimum bits << 32) | sub-block that produced it;
                     //                            one slot per CTA that covered the (pair, strip)
     u64* colpart;   // [B*strips][4 warps][Mpad]  (min bits << 32) | ballot of lanes attaining it
-    unsigned* counters;  // [B] arrival counters of the finalize kernel's loss reduction; zeroed here (or nullptr)
+    unsigned* counters;  // [B + 1] arrival counters of the finalize kernel's loss reductions; zeroed here (or nullptr)
     int B;
 };
 
@@ -208,7 +207,7 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
 
     cudaGridDependencySynchronize();  // (PDL) the producer of p1/p2 and the previous user of the workspace are done
     if (g == 0 && a.counters)
-        for (int q = tid; q < a.B; q += kSweepThreads) a.counters[q] = 0u;
+        for (int q = tid; q <= a.B; q += kSweepThreads) a.counters[q] = 0u;
     // let the finalize grid be scheduled onto SMs as this grid's CTAs retire (it waits for our completion itself)
     cudaTriggerProgrammaticLaunchCompletion();
 
@@ -216,7 +215,7 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
         const int b_ = a.strips == 1 ? bs_ : bs_ / a.strips;
         const int cb = cu_ * kUnit;
         const int n = (min(a.M, cb + n_ * kUnit) - cb) * 3;
-        const float* src = a.p2 + ((size_t)b_ * a.M + cb) * 3;
+        const float* src = seg_p2(a.seg, b_, a.M) + (size_t)cb * 3;
 #pragma unroll
         for (int q = 0; q < kPf; ++q) pf[q] = lane + 32 * q < n ? __ldg(src + lane + 32 * q) : CUDART_INF_F;
     };
@@ -251,7 +250,7 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
             b = a.strips == 1 ? bs : bs / a.strips;
             strip = bs - b * a.strips;
             slot = g - cta_of_unit(bs * a.ups, a.q, a.r);
-            const float* p1b = a.p1 + (size_t)b * a.N * 3;
+            const float* p1b = seg_p1(a.seg, b, a.N);
             const int row0 = strip * (kSweepThreads * R) + tid * R;
             const float* rsrc = p1b + 3 * (size_t)row0;
             if (row0 + R <= a.N && (reinterpret_cast<uintptr_t>(rsrc) & 15) == 0) {
@@ -419,8 +418,7 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
 // finalize
 // ---------------------------------------------------------------------------------------------------------
 struct FinalizeArgs {
-    const float* p1;
-    const float* p2;
+    SegTable seg;
     int N, M, R, strips, ups, q, r, maxslots, Mpad;
     const u64* rowpart;
     const u64* colpart;
@@ -429,10 +427,12 @@ struct FinalizeArgs {
     int64_t* idx1;
     int64_t* idx2;
     double* losspart;    // per-CTA sums of the distances (nullptr: no loss wanted)
-    unsigned* counters;  // per-pair arrival counters, zeroed by the sweep kernel
+    unsigned* counters;  // per-pair arrival counters + one for the whole batch, zeroed by the sweep kernel
     float* loss;
     float w1, w2;
     int nrb, ncb;
+    float* totals;       // [1 + segments]: weighted total and per-segment sums of loss (nullptr: not wanted)
+    int B;
 };
 
 __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const FinalizeArgs a) {
@@ -444,8 +444,8 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int b = blockIdx.y, blk = blockIdx.x;
-    const float* __restrict__ p1b = a.p1 + (size_t)b * a.N * 3;
-    const float* __restrict__ p2b = a.p2 + (size_t)b * a.M * 3;
+    const float* __restrict__ p1b = seg_p1(a.seg, b, a.N);
+    const float* __restrict__ p2b = seg_p2(a.seg, b, a.M);
     const int TN = kSweepThreads * a.R;
     float mine = 0.f;  // this thread's distance, for the loss partial
     cudaTriggerProgrammaticLaunchCompletion();  // a following backward may start to launch
@@ -614,6 +614,30 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
                 s2 += __shfl_down_sync(0xffffffffu, s2, o);
             }
             if (lane == 0) a.loss[b] = (float)((double)a.w1 * (s1 / a.N) + (double)a.w2 * (s2 / a.M));
+            if (a.totals) {
+                // the reduction on top (few_shot.py:110,117,121): whichever pair finishes last adds the per-pair
+                // losses in index order, per segment, in double -- again independent of arrival order
+                bool last = false;
+                if (lane == 0) {
+                    __threadfence();
+                    last = atomicAdd(a.counters + a.B, 1u) == (unsigned)(a.B - 1);
+                }
+                if (__shfl_sync(0xffffffffu, last, 0)) {
+                    __threadfence();
+                    const volatile float* lv = a.loss;
+                    double total = 0.0;
+                    for (int sg = 0; sg < a.seg.n; ++sg) {
+                        double acc = 0.0;
+                        for (int q = a.seg.b0[sg] + lane; q < a.seg.b0[sg + 1]; q += 32) acc += (double)lv[q];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+                        acc = __shfl_sync(0xffffffffu, acc, 0);
+                        if (lane == 0) a.totals[1 + sg] = (float)acc;
+                        total += (double)a.seg.weight[sg] * (double)(float)acc;
+                    }
+                    if (lane == 0) a.totals[0] = (float)total;
+                }
+            }
         }
     }
 }
@@ -623,12 +647,15 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
 // ---------------------------------------------------------------------------------------------------------
 // sweep_only: launch just the sweep kernel (partials land in the workspace); bench.py times the dominant kernel
 // alone this way for the roofline line.
-int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M, float* dist1, float* dist2,
-                           int64_t* idx1, int64_t* idx2, float* loss, float w1, float w2, void* ws, size_t ws_bytes,
+int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
+                           int64_t* idx2, float* loss, float* totals, float w1, float w2, void* ws, size_t ws_bytes,
                            cudaStream_t stream, bool sweep_only) {
     if (B < 0 || N < 1 || M < 1) return fail(FPSG_EINVAL, "chamfer: need B >= 0, N >= 1, M >= 1 (got B=%d N=%d M=%d)", B, N, M);
     if (B == 0) return FPSG_OK;
-    if (!p1 || !p2 || (!sweep_only && (!idx1 || !idx2))) return fail(FPSG_EINVAL, "chamfer: null p1/p2/idx1/idx2");
+    for (int sg = 0; sg < seg.n; ++sg)
+        if (seg.b0[sg + 1] > seg.b0[sg] && (!seg.p1[sg] || !seg.p2[sg])) return fail(FPSG_EINVAL, "chamfer: null p1/p2");
+    if (!sweep_only && (!idx1 || !idx2)) return fail(FPSG_EINVAL, "chamfer: null idx1/idx2");
+    if (totals && !loss) return fail(FPSG_EINVAL, "chamfer: totals need the per-pair loss buffer");
     if (B > 65535) return fail(FPSG_EINVAL, "chamfer: B > 65535 not supported in one call");
     if ((long long)N * 3 > 0x7fffffffLL || (long long)M * 3 > 0x7fffffffLL) return fail(FPSG_EINVAL, "chamfer: cloud too large");
     const ChamferPlan pl = make_chamfer_plan(B, N, M);
@@ -642,7 +669,7 @@ int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M
     double* losspart = loss ? reinterpret_cast<double*>(base + pl.losspart_off) : nullptr;
     unsigned* counters = loss ? reinterpret_cast<unsigned*>(base + pl.counters_off) : nullptr;
 
-    const SweepArgs sa{p1, p2, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart, counters, B};
+    const SweepArgs sa{seg, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart, counters, B};
     const dim3 sgrid((unsigned)pl.grid), sblock(kSweepThreads);
     if (pl.R == 16 && pl.packed)
         FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<16, true>, sgrid, sblock, 0, stream, sa));
@@ -653,8 +680,8 @@ int chamfer_forward_launch(const float* p1, const float* p2, int B, int N, int M
     else
         FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<4, false>, sgrid, sblock, 0, stream, sa));
     if (sweep_only) return FPSG_OK;
-    const FinalizeArgs fa{p1, p2, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart,
-                          dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb};
+    const FinalizeArgs fa{seg, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart,
+                          dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb, totals, B};
     const dim3 fgrid((unsigned)(pl.nrb + pl.ncb), (unsigned)B);
     FPSG_CUDA_OK(launch_pdl(chamfer_finalize_kernel, fgrid, dim3(kFinThreads), 0, stream, fa));
     FPSG_CUDA_OK(cudaGetLastError());

@@ -24,6 +24,52 @@ int fail(int code, const char* fmt, ...);
 constexpr size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// A batch made of up to FPSG_MAX_SEGMENTS separately allocated runs of pairs ("segments": the query-set and
+// support-set calls of the reference's training loss, src/models/few_shot.py:109-117). Pair b of the batch lives in
+// segment s = the last one with b0[s] <= b, at local index b - b0[s]. A plain (B,N,3)/(B,M,3) call is one segment.
+struct SegTable {
+    const float* p1[FPSG_MAX_SEGMENTS];
+    const float* p2[FPSG_MAX_SEGMENTS];
+    float* gp1[FPSG_MAX_SEGMENTS];  // backward only
+    float* gp2[FPSG_MAX_SEGMENTS];
+    int b0[FPSG_MAX_SEGMENTS + 1];  // b0[n] = total number of pairs
+    float weight[FPSG_MAX_SEGMENTS];
+    int n;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int seg_find(const SegTable& t, int b) {
+    int s = 0;
+#pragma unroll
+    for (int q = 1; q < FPSG_MAX_SEGMENTS; ++q) s += (q < t.n && b >= t.b0[q]) ? 1 : 0;
+    return s;
+}
+// cloud b of the p1 / p2 side (npts points of 3 floats per cloud)
+__device__ __forceinline__ const float* seg_p1(const SegTable& t, int b, int npts) {
+    if (t.n == 1) return t.p1[0] + (size_t)b * npts * 3;
+    const int s = seg_find(t, b);
+    return t.p1[s] + (size_t)(b - t.b0[s]) * npts * 3;
+}
+__device__ __forceinline__ const float* seg_p2(const SegTable& t, int b, int npts) {
+    if (t.n == 1) return t.p2[0] + (size_t)b * npts * 3;
+    const int s = seg_find(t, b);
+    return t.p2[s] + (size_t)(b - t.b0[s]) * npts * 3;
+}
+#endif
+
+inline SegTable single_segment(const float* p1, const float* p2, float* gp1, float* gp2, int B) {
+    SegTable t = {};
+    t.p1[0] = p1;
+    t.p2[0] = p2;
+    t.gp1[0] = gp1;
+    t.gp2[0] = gp2;
+    t.b0[0] = 0;
+    t.b0[1] = B;
+    t.weight[0] = 1.0f;
+    t.n = 1;
+    return t;
+}
+
 // The canonical FP32 squared distance (oracle/fpsg_oracle.c sqdist_f32): differences, then
 // t = rn(dy*dy); t = fma(dx,dx,t); d = fma(dz,dz,t). The *_rn intrinsics are never re-associated or
 // re-contracted by nvcc, so the bits match the oracle's fmaf() chain exactly.

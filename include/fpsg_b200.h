@@ -15,6 +15,9 @@
  *   fpsg_chamfer_loss_fwd / fpsg_chamfer_loss_bwd
  *       the same plus the reduction glue `w1*mean + w2*mean` and the uniform upstream gradient produced by
  *       `.sum()` at src/models/few_shot.py:110,117.
+ *   fpsg_chamfer_multi_loss_fwd / fpsg_chamfer_multi_loss_bwd
+ *       both Chamfer calls of one training step (query set :110, support set :117), their `.sum()`s and the
+ *       weighted total (:121-122) in one launch chain.
  *   fpsg_knn_fwd
  *       `knn(x, k)` at src/dgcnn/model.py:13-20 (called from get_graph_feature, :28).
  *   fpsg_edge_feature_fwd / fpsg_edge_feature_bwd
@@ -70,6 +73,32 @@ int fpsg_chamfer_loss_fwd(const float* p1, const float* p2, int B, int N, int M,
 int fpsg_chamfer_loss_bwd(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2,
                           const float* gloss, float w1, float w2, int B, int N, int M, float* gp1, float* gp2,
                           void* ws, size_t ws_bytes, fpsg_stream_t stream);
+
+/* Several separately allocated runs of pairs ("segments") in ONE launch chain, plus the reduction the reference
+ * applies on top: the query-set and support-set calls of the training loss and their weighted sum,
+ *     loss_rec_q = pc_metric(syn_q, ref_q).sum(); loss_rec_s = pc_metric(syn_s, ref_s).sum()
+ *     ttl_loss   = query_factor * loss_rec_q + support_factor * loss_rec_s      (src/models/few_shot.py:109-122)
+ * (the dual-call batching half). All segments share N and M. `segs_host` is a HOST array
+ * read during the call. loss (Btot,) per-pair values in segment order, Btot = sum of batch; totals (1 + nseg,):
+ * totals[0] = sum_s weight_s * sum_{b in s} loss[b], totals[1 + s] = sum_{b in s} loss[b]; idx1 (Btot,N),
+ * idx2 (Btot,M). Workspace: fpsg_chamfer_fwd_workspace_bytes(Btot, N, M). */
+#define FPSG_MAX_SEGMENTS 8
+typedef struct fpsg_chamfer_segment {
+    const float* p1; /* (batch, N, 3) */
+    const float* p2; /* (batch, M, 3) */
+    float* gp1;      /* backward only: (batch, N, 3), or NULL = not requested */
+    float* gp2;      /* backward only: (batch, M, 3), or NULL = not requested */
+    int batch;       /* >= 0 */
+    float weight;    /* factor of this segment's summed loss in totals[0] */
+} fpsg_chamfer_segment_t;
+int fpsg_chamfer_multi_loss_fwd(const fpsg_chamfer_segment_t* segs_host, int nseg, int N, int M, float w1, float w2,
+                                float* loss, float* totals, int64_t* idx1, int64_t* idx2, void* ws, size_t ws_bytes,
+                                fpsg_stream_t stream);
+/* gtotal: DEVICE scalar, the upstream gradient of totals[0]; every pair of segment s receives
+ * gloss = gtotal * weight_s, then as fpsg_chamfer_loss_bwd. Gradients go to each segment's gp1 / gp2. */
+int fpsg_chamfer_multi_loss_bwd(const fpsg_chamfer_segment_t* segs_host, int nseg, const int64_t* idx1,
+                                const int64_t* idx2, const float* gtotal, float w1, float w2, int N, int M,
+                                fpsg_stream_t stream);
 
 /* ---- kNN graph ------------------------------------------------------------------------------------------ */
 /* x (B,C,N) channel-major FP32; idx (B,N,k) int64: the k nearest points of every point (self included),

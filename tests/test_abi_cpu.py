@@ -40,6 +40,20 @@ def test_invalid_arguments_are_reported_not_crashed():
         _lib.check(rc)
 
 
+def test_multi_segment_argument_checks_need_no_gpu():
+    L = _lib.lib()
+    segs = (_lib.ChamferSegment * 2)()
+    assert L.fpsg_chamfer_multi_loss_fwd(segs, 0, 8, 8, 1.0, 1.0, None, None, None, None, None, 0, None) == -1
+    assert L.fpsg_chamfer_multi_loss_fwd(segs, _lib.MAX_SEGMENTS + 1, 8, 8, 1.0, 1.0, None, None, None, None, None, 0, None) == -1
+    segs[0].batch = -1
+    assert L.fpsg_chamfer_multi_loss_fwd(segs, 2, 8, 8, 1.0, 1.0, None, None, None, None, None, 0, None) == -1
+    assert b"batch" in L.fpsg_last_error()
+    segs[0].batch = 0
+    assert L.fpsg_chamfer_multi_loss_bwd(segs, 2, None, None, None, 1.0, 1.0, 8, 8, None) == -1  # null gtotal
+    import ctypes as C
+    assert C.sizeof(_lib.ChamferSegment) == 40  # 4 pointers + int + float, as the C struct
+
+
 def test_host_code_refuses_cpu_tensors():
     import fpsg_b200
     with pytest.raises(RuntimeError, match="CUDA"):
