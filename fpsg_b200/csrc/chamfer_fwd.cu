@@ -234,18 +234,9 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
             ++nbs;
         }
 
-        // park the prefetched tile in this warp's shared-memory buffer
-        __syncwarp();  // all lanes are done reading the previous tile
-        if (PACKED) {
-#pragma unroll
-            for (int q = 0; q < kPf; ++q) *reinterpret_cast<float2*>(&sCols[w][pk_off[q]]) = make_float2(pf[q], pf[q]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < kPf; ++q) sCols[w][lane + 32 * q] = pf[q];
-        }
-
         if (bs != cur_bs) {
-            // new (pair, strip): bring this thread's R consecutive rows into registers
+            // new (pair, strip): bring this thread's R consecutive rows into registers. Issued before the tile is parked, so
+            // that the two global-memory latencies (rows here, prefetched columns below) overlap instead of adding up
             cur_bs = bs;
             b = a.strips == 1 ? bs : bs / a.strips;
             strip = bs - b * a.strips;
@@ -288,6 +279,16 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
                 }
             }
         }
+        // park the prefetched tile in this warp's shared-memory buffer
+        __syncwarp();  // all lanes are done reading the previous tile
+        if (PACKED) {
+#pragma unroll
+            for (int q = 0; q < kPf; ++q) *reinterpret_cast<float2*>(&sCols[w][pk_off[q]]) = make_float2(pf[q], pf[q]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < kPf; ++q) sCols[w][lane + 32 * q] = pf[q];
+        }
+
         __syncwarp();  // tile visible to the whole warp
         if (nleft > 0) fetch(nbs, ncu, piece_units(ncu, nleft));  // overlaps the whole sub-block below
 
