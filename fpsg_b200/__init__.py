@@ -7,6 +7,8 @@ forward/backward and the DGCNN kNN graph, behind the reference's own call surfac
 from .chamfer import chamfer_distance, chamfer_loss, chamfer_loss_multi, sided_distance
 from .graph_feature import get_graph_feature
 from .knn import knn
+from .pointcloud_io import normalize_point_clouds, ply_reader
 
-__all__ = ["chamfer_distance", "chamfer_loss", "chamfer_loss_multi", "sided_distance", "knn", "get_graph_feature"]
+__all__ = ["chamfer_distance", "chamfer_loss", "chamfer_loss_multi", "sided_distance", "knn", "get_graph_feature", "ply_reader",
+           "normalize_point_clouds"]
 __version__ = "0.1.0"

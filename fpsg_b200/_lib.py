@@ -64,6 +64,10 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_edge_feature_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     L.fpsg_edge_feature_bwd.restype = c_int
     L.fpsg_edge_feature_bwd.argtypes = [vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]
+    L.fpsg_normalize_clouds.restype = c_int
+    L.fpsg_normalize_clouds.argtypes = [vp, c_int, c_int, vp, vp]
+    L.fpsg_ply_read_ascii_host.restype = c_int
+    L.fpsg_ply_read_ascii_host.argtypes = [ctypes.c_char_p, c_int, vp, ctypes.POINTER(c_int)]
     L.fpsg_chamfer_sweep_only.restype = c_int
     L.fpsg_chamfer_sweep_only.argtypes = [vp, vp, c_int, c_int, c_int, vp, c_size_t, vp]
     L.fpsg_probe_fp32_peak.restype = c_int

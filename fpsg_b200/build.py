@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfpsg_b200.so")
-SOURCES = ["api.cu", "chamfer_fwd.cu", "chamfer_bwd.cu", "knn.cu", "edge_feature.cu"]
+SOURCES = ["api.cu", "chamfer_fwd.cu", "chamfer_bwd.cu", "knn.cu", "edge_feature.cu", "pointcloud_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-cudart", "static", "-diag-suppress", "550"]
 

@@ -50,6 +50,8 @@ int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C
 size_t edge_feature_backward_workspace(int B, int C, int N, int k);
 int edge_feature_backward_launch(const float* g, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws, size_t ws_bytes,
                                  cudaStream_t stream);
+int normalize_clouds_launch(const float* in, int B, int N, float* out, cudaStream_t stream);
+int ply_read_ascii(const char* path, int max_points, float* xyz, int* n_points);
 size_t knn_workspace(int B, int C, int N, int k);
 int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t stream);
 
@@ -169,6 +171,14 @@ size_t fpsg_edge_feature_bwd_workspace_bytes(int B, int C, int N, int k) { retur
 int fpsg_edge_feature_bwd(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws, size_t ws_bytes,
                           fpsg_stream_t stream) {
     return edge_feature_backward_launch(gout, idx, B, C, N, k, gx, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int fpsg_normalize_clouds(const float* in, int B, int N, float* out, fpsg_stream_t stream) {
+    return normalize_clouds_launch(in, B, N, out, static_cast<cudaStream_t>(stream));
+}
+
+int fpsg_ply_read_ascii_host(const char* path, int max_points, float* xyz_host, int* n_points_host) {
+    return ply_read_ascii(path, max_points, xyz_host, n_points_host);
 }
 
 int fpsg_probe_fp32_peak(double* tflops_host, double* sm_mhz_host, fpsg_stream_t stream_) {

@@ -452,6 +452,26 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
     cudaTriggerProgrammaticLaunchCompletion();  // a following backward may start to launch
     cudaGridDependencySynchronize();            // the sweep's partials are complete and visible from here on
 
+    // Loss partial of this CTA: needs only the merged minima, so it is issued before the arg-min re-evaluation and
+    // the latency of the arrival-counter atomic hides behind that phase. Fixed-order block sum in double (lanes by
+    // shuffle tree, warps ascending).
+    const int nblk = a.nrb + a.ncb;
+    unsigned ticket = 0u;
+    auto loss_partial = [&](float mine) {
+        double v = (double)mine;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sRed[w] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int q = 0; q < kFinThreads / 32; ++q) s += sRed[q];
+            a.losspart[(size_t)b * nblk + blk] = s;
+            __threadfence();
+            ticket = atomicAdd(a.counters + b, 1u);
+        }
+    };
+
     if (blk < a.nrb) {
         // ---- rows: each thread merges the partials of the CTAs that covered its row's strip ... ----
         const int i = blk * kFinThreads + tid;
@@ -486,6 +506,7 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
         sPt[tid] = make_float4(ax, ay, az, m);
         sBase[tid] = sub * kSub;
         __syncwarp();
+        if (a.losspart) loss_partial(mine);
         // ... then the warp re-evaluates the kSub columns of every row's winning sub-block together (coalesced);
         // the lowest lane whose distance equals the minimum bit-for-bit is the arg-min. Lanes past the end of the
         // cloud re-evaluate the last column: they can only tie with a lower lane that holds the same column.
@@ -554,6 +575,7 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
         sPt[tid] = make_float4(qx, qy, qz, m);
         sBase[tid] = r0;
         __syncwarp();
+        if (a.losspart) loss_partial(mine);
         // ... then groups of R lanes re-evaluate the R consecutive rows of each column's winning thread (coalesced)
         const int R = a.R, per = 32 / R, grp = lane / R, off = lane - grp * R;
         const unsigned gmask = ((1u << R) - 1u) << (grp * R);  // R <= 16
@@ -587,21 +609,9 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
     }
 
     if (a.losspart) {
-        // fixed-order block sum in double (lanes by shuffle tree, warps ascending); the last CTA of the pair to
-        // arrive adds the per-CTA sums in index order, so the result does not depend on arrival order
-        double v = (double)mine;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) sRed[w] = v;
-        __syncthreads();
-        const int nblk = a.nrb + a.ncb;
-        if (tid == 0) {
-            double s = 0.0;
-            for (int q = 0; q < kFinThreads / 32; ++q) s += sRed[q];
-            a.losspart[(size_t)b * nblk + blk] = s;
-            __threadfence();
-            sLast = atomicAdd(a.counters + b, 1u) == (unsigned)(nblk - 1);
-        }
+        // the last CTA of the pair to arrive adds the per-CTA sums in index order, so the result does not depend on
+        // arrival order
+        if (tid == 0) sLast = ticket == (unsigned)(nblk - 1);
         __syncthreads();
         if (sLast && w == 0) {
             __threadfence();

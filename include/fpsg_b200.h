@@ -24,6 +24,10 @@
  *       the gather / repeat / cat / permute tail of `get_graph_feature`, src/dgcnn/model.py:31-41, and its
  *       autograd backward.
  *
+ *   fpsg_normalize_clouds / fpsg_ply_read_ascii_host
+ *       the host input pipeline in front of the path: `ply_reader` (src/datasets/modelnet.py:15-29) and the
+ *       centre / scale block of `FewShotSubModelNet.__getitem__` (:66-69).
+ *
  * INTEGRATION.md shows the reference-side bindings (ctypes) a maintainer would add.
  */
 #ifndef FPSG_B200_H_
@@ -120,6 +124,15 @@ int fpsg_edge_feature_fwd(const float* x, const int64_t* idx, int B, int C, int 
 size_t fpsg_edge_feature_bwd_workspace_bytes(int B, int C, int N, int k);
 int fpsg_edge_feature_bwd(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws,
                           size_t ws_bytes, fpsg_stream_t stream);
+
+/* ---- Point-cloud input pipeline ---------------------------------------------------- */
+/* The per-item normalisation of `FewShotSubModelNet.__getitem__` (src/datasets/modelnet.py:66-69) for a whole
+ * batch on the device: out[b] = (in[b] - mean_i in[b,i]) / max_i |in[b,i] - mean|, in/out (B,N,3) FP32, bit-identical
+ * to the reference's numpy float32 arithmetic (rows summed in order). in and out must not overlap. */
+int fpsg_normalize_clouds(const float* in, int B, int N, float* out, fpsg_stream_t stream);
+/* `ply_reader` (src/datasets/modelnet.py:15-29): reads at most max_points (the reference uses 2048) xyz vertices
+ * of an ASCII PLY file into xyz_host (max_points*3 floats, HOST memory); *n_points_host receives the count. */
+int fpsg_ply_read_ascii_host(const char* path, int max_points, float* xyz_host, int* n_points_host);
 
 /* ---- Profiling hooks (used by bench.py for the roofline line; not part of the reference-facing surface) ---- */
 /* Launches only K1's sweep kernel (the dominant kernel) with the workspace of fpsg_chamfer_fwd; the partial

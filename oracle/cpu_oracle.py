@@ -44,6 +44,7 @@ def lib() -> ctypes.CDLL:
                                              ctypes.c_int, _f32p, _f32p]
         L.oracle_knn_f32.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i64p, _f32p]
         L.oracle_knn_pd_f64.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p]
+        L.oracle_normalize_clouds_f32.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, _f32p]
         for name in ("oracle_sided_distance_f32", "oracle_sided_distance_f64", "oracle_chamfer_fwd_f32",
                      "oracle_chamfer_bwd_f32", "oracle_knn_f32", "oracle_knn_pd_f64", "oracle_set_threads"):
             getattr(L, name).restype = None
@@ -161,3 +162,29 @@ def knn_pd_f64(x):
     if B * N:
         lib().oracle_knn_pd_f64(_p(x, _f32p), B, C, N, _p(pd, _f64p))
     return pd
+
+
+def normalize_clouds(x):
+    """(B,N,3) float32 -> every cloud centred on its mean point and divided by its largest point norm, in numpy's
+    float32 arithmetic (reference src/datasets/modelnet.py:66-69)."""
+    x = _f32(x)
+    assert x.ndim == 3 and x.shape[2] == 3
+    out = np.empty_like(x)
+    if x.shape[0] and x.shape[1]:
+        lib().oracle_normalize_clouds_f32(_p(x, _f32p), x.shape[0], x.shape[1], _p(out, _f32p))
+    return out
+
+
+def ply_reader_py(file_path, n_verts=2048):
+    """ply_reader of the reference (src/datasets/modelnet.py:15-29), restated line for line in Python: the checker
+    of the C parser (the real function's outputs are in tests/golden/pipeline_ply.npz)."""
+    with open(file_path, "r") as f:
+        while True:
+            cur = f.readline().strip()
+            if cur == "end_header":
+                break
+            cur = cur.split(" ")
+            if len(cur) > 2 and cur[1] == "vertex":
+                n_verts = min(int(cur[2]), n_verts)
+        vertices = [[float(s) for s in f.readline().strip().split(" ")] for _ in range(n_verts)]
+    return np.asarray(vertices, dtype=np.float32)
