@@ -47,16 +47,33 @@ __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+__device__ __forceinline__ void cp_async_f32x4(float* smem_dst, const float* gmem_src) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
 // loads the [C][jn] block x[:, j0:j0+jn] and the matching squared norms into shared memory (row stride J)
 __device__ __forceinline__ void knn_load_tile(float* sTile, float* sXX, const float* __restrict__ xb, const float* __restrict__ xxb,
                                               int C, int N, int J, int j0, int jn, int tid, int nthreads = kKnnThreads) {
     const int lane = tid & 31, w = tid >> 5, nwarps = nthreads >> 5;
-    for (int c = w; c < C; c += nwarps) {  // a warp copies whole channel rows: coalesced, no index arithmetic
-        const float* src = xb + (size_t)c * N + j0;
-        float* dst = sTile + (size_t)c * J;
-        for (int jj = lane; jj < jn; jj += 32) cp_async_f32(dst + jj, src + jj);
+    // 16-byte copies when every row segment is 16-byte aligned on both sides (J is always a multiple of 32)
+    const bool vec = ((N | j0 | jn) & 3) == 0 && (reinterpret_cast<uintptr_t>(xb) & 15) == 0 && (reinterpret_cast<uintptr_t>(xxb) & 15) == 0;
+    if (vec) {
+        const int jq = jn >> 2;
+        for (int c = w; c < C; c += nwarps) {
+            const float* src = xb + (size_t)c * N + j0;
+            float* dst = sTile + (size_t)c * J;
+            for (int jj = lane; jj < jq; jj += 32) cp_async_f32x4(dst + 4 * jj, src + 4 * jj);
+        }
+        for (int jj = tid; jj < jq; jj += nthreads) cp_async_f32x4(sXX + 4 * jj, xxb + j0 + 4 * jj);
+    } else {
+        for (int c = w; c < C; c += nwarps) {  // a warp copies whole channel rows: coalesced, no index arithmetic
+            const float* src = xb + (size_t)c * N + j0;
+            float* dst = sTile + (size_t)c * J;
+            for (int jj = lane; jj < jn; jj += 32) cp_async_f32(dst + jj, src + jj);
+        }
+        for (int jj = tid; jj < jn; jj += nthreads) cp_async_f32(sXX + jj, xxb + j0 + jj);
     }
-    for (int jj = tid; jj < jn; jj += nthreads) cp_async_f32(sXX + jj, xxb + j0 + jj);
     cp_async_wait_all();
 }
 
@@ -862,6 +879,167 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Generic channel count, k <= 32: threshold selection around an undisturbed FP32 contraction (DGCNN layers 2-4:
+// C = 64, 64, 128). The register-tiled inner product of knn_gemm_kernel (8 queries x 128 candidates per warp step)
+// runs with NO selection in the loop: a lane streams the four scores of each query to a scratch row in the
+// workspace (one coalesced 512-byte store per query and step) and keeps the running maximum of everything it
+// has scored for that query. When the cloud is done, the 32 lane maxima of a query are the maxima of 32 disjoint
+// candidate groups, so their k-th largest value T (warp bitonic sort) is a lower bound of the k-th largest
+// score. Every lane then re-reads the scores it wrote itself (still in L2), the ones >= T (about 31 for k = 20,
+// N = 1024) are compacted into (pd, index) keys, sorted, and the first k indices written. More than 64
+// candidates >= T (massive ties) -> streaming sort-and-merge over the scratch row. Nothing is computed twice;
+// the scratch traffic (4 N^2 bytes per cloud, written once and read once) replaces the reference's three (B,N,N)
+// temporaries and its radix top-k, and stays far below the FP32 time of the contraction.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sort_desc_f32(float v, int lane) {
+#pragma unroll
+    for (int s = 2; s <= 32; s <<= 1) {
+        const bool desc = s == 32 ? true : ((lane & s) == 0);
+#pragma unroll
+        for (int d = s >> 1; d > 0; d >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, v, d);
+            v = (((lane & d) == 0) == desc) ? fmaxf(v, o) : fminf(v, o);
+        }
+    }
+    return v;
+}
+
+constexpr int kRowsThreads = 256, kRowsWarps = kRowsThreads / 32;  // two CTAs per SM: one computes while the other loads a tile
+
+__global__ void __launch_bounds__(kRowsThreads, 2)
+knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int k, int J, int npad, float* __restrict__ rows,
+                int64_t* __restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sTile = reinterpret_cast<float*>(smem_raw);  // [C][J], J a multiple of 128
+    float* sXX = sTile + (size_t)C * J;                 // [J]
+    float* sQ = sXX + J;                                // [kRowsWarps][C][kKnnQB]
+    u64* sKey = reinterpret_cast<u64*>(sQ + (size_t)kRowsWarps * C * kKnnQB);  // [kRowsWarps][64]
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int b = blockIdx.y;
+    const int i0 = (blockIdx.x * kRowsWarps + w) * kKnnQB;
+    const float* __restrict__ xb = x + (size_t)b * C * N;
+    const float* __restrict__ xxb = xx + (size_t)b * N;
+    float* myQ = sQ + (size_t)w * C * kKnnQB;
+    u64* myKey = sKey + w * kSelCap;
+    float* myRows = rows + ((size_t)b * N + min(i0, N - 1)) * npad + 4 * lane;  // + q * npad + step * 128
+
+    float xxi[kKnnQB], cm[kKnnQB];
+#pragma unroll
+    for (int q = 0; q < kKnnQB; ++q) {
+        xxi[q] = __ldg(xxb + min(i0 + q, N - 1));
+        cm[q] = -CUDART_INF_F;
+    }
+    for (int e = lane; e < C * kKnnQB; e += 32) {
+        const int c = e / kKnnQB, q = e - c * kKnnQB;
+        myQ[e] = __ldg(xb + (size_t)c * N + min(i0 + q, N - 1));
+    }
+    __syncwarp();
+
+    for (int j0 = 0; j0 < N; j0 += J) {
+        const int jn = min(J, N - j0);
+        __syncthreads();  // previous tile fully consumed
+        knn_load_tile(sTile, sXX, xb, xxb, C, N, J, j0, jn, tid, kRowsThreads);
+        __syncthreads();
+        if (i0 >= N) continue;  // warp-uniform; the warp still takes part in the barriers
+
+        for (int jb = 0; jb < jn; jb += 32 * kKnnTC) {
+            const int jl = jb + kKnnTC * lane;  // this lane's first candidate inside the tile
+            float dot[kKnnQB][kKnnTC];
+#pragma unroll
+            for (int q = 0; q < kKnnQB; ++q)
+#pragma unroll
+                for (int t = 0; t < kKnnTC; ++t) dot[q][t] = 0.f;
+            const float* tp = sTile + jl;
+#pragma unroll 2
+            for (int c = 0; c < C; ++c) {
+                const float4 cv = *reinterpret_cast<const float4*>(tp + (size_t)c * J);
+                const float4 qa = *reinterpret_cast<const float4*>(myQ + c * kKnnQB);
+                const float4 qb = *reinterpret_cast<const float4*>(myQ + c * kKnnQB + 4);
+                const float qv[kKnnQB] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                const float cc[kKnnTC] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                for (int q = 0; q < kKnnQB; ++q)
+#pragma unroll
+                    for (int t = 0; t < kKnnTC; ++t) dot[q][t] = __fmaf_rn(qv[q], cc[t], dot[q][t]);
+            }
+            const float4 nx = *reinterpret_cast<const float4*>(sXX + jl);
+            const float nxx[kKnnTC] = {-nx.x, -nx.y, -nx.z, -nx.w};
+            float* out = myRows + (j0 + jb);
+#pragma unroll
+            for (int q = 0; q < kKnnQB; ++q) {
+                float pd[kKnnTC];
+#pragma unroll
+                for (int t = 0; t < kKnnTC; ++t)
+                    pd[t] = jl + t < jn ? __fsub_rn(__fmaf_rn(2.0f, dot[q][t], nxx[t]), xxi[q]) : -CUDART_INF_F;  // padding never wins
+                cm[q] = max3(max3(cm[q], pd[0], pd[1]), pd[2], pd[3]);
+                if (i0 + q < N) *reinterpret_cast<float4*>(out + (size_t)q * npad) = make_float4(pd[0], pd[1], pd[2], pd[3]);
+            }
+        }
+    }
+    if (i0 >= N) return;
+
+    // ---- selection: per query, threshold from the 32 lane maxima, then this lane's own scores again ----
+#pragma unroll 1
+    for (int q = 0; q < kKnnQB; ++q) {
+        if (i0 + q >= N) break;  // warp-uniform
+        float mine = cm[0];      // cm[q] without dynamic register indexing
+#pragma unroll
+        for (int z = 1; z < kKnnQB; ++z) mine = z == q ? cm[z] : mine;
+        const float thr = __shfl_sync(0xffffffffu, warp_sort_desc_f32(mine, lane), k - 1);
+        const float* row = myRows + (size_t)q * npad;
+        int cnt = 0;
+        __syncwarp();  // the previous query's keys are no longer read
+        for (int s0 = 0; s0 < npad; s0 += 128) {
+            const float4 p4 = *reinterpret_cast<const float4*>(row + s0);
+            const float p[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = s0 + 4 * lane + t;
+                const bool pass = j < N && p[t] >= thr;
+                const unsigned m = __ballot_sync(0xffffffffu, pass);
+                if (m) {  // warp-uniform
+                    const int pos = cnt + __popc(m & lt_mask);
+                    if (pass && pos < kSelCap) myKey[pos] = knn_key_of(p[t], j);
+                    cnt += __popc(m);
+                }
+            }
+        }
+        __syncwarp();
+        u64 key = 0ull;
+        if (cnt <= kSelCap) {
+            for (int h = 0; h * 32 < cnt; ++h) {
+                const int e = h * 32 + lane;
+                const u64 kb = warp_sort_desc(e < cnt ? myKey[e] : 0ull, lane);
+                if (h == 0) {
+                    key = kb;
+                } else {
+                    const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
+                    key = warp_merge_desc(key > rev ? key : rev, lane);
+                }
+            }
+        } else {
+            // more than 64 candidates tie with the threshold: streaming sort-and-merge over the scratch row
+            const float* rowq = rows + ((size_t)b * N + i0 + q) * npad;  // other lanes' stores: visible after the __syncwarp above
+            u64 tau = 0ull;
+            for (int j0 = 0; j0 < N; j0 += 32) {
+                const int j = j0 + lane;
+                u64 kb = j < N ? knn_key_of(__ldcg(rowq + j), j) : 0ull;
+                if (!(kb > tau)) kb = 0ull;
+                if (__any_sync(0xffffffffu, kb != 0ull)) {
+                    kb = warp_sort_desc(kb, lane);
+                    const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
+                    key = warp_merge_desc(key > rev ? key : rev, lane);
+                    tau = __shfl_sync(0xffffffffu, key, k - 1);
+                }
+            }
+        }
+        if (lane < k) idx[((size_t)b * N + i0 + q) * k + lane] = (int64_t)(0xffffffffu - (unsigned)key);
+    }
+}
+
 static int sm_count_knn() {
     static int n = 0;
     if (n == 0) {
@@ -874,6 +1052,8 @@ static int sm_count_knn() {
 
 struct KnnPlan {
     int KR;
+    bool rows;   // generic C, k <= 32: knn_rows_kernel (scores streamed to scratch rows in the workspace)
+    int npad;    // floats per scratch row
     bool gemm;  // generic C, k <= 32: the register-tiled scoring kernel
     int J;
     size_t smem;
@@ -890,6 +1070,8 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
     if (j > npad) j = npad;
     p.J = (int)j;
     p.gemm = false;
+    p.rows = false;
+    p.npad = 0;
     if (p.KR == 1 && C != 3 && !getenv("FPSG_KNN_INSERT") && !getenv("FPSG_KNN_NOGEMM")) {
         long long jg = (long long)(kKnnTileBytes / sizeof(float)) / (C + 1) / 128 * 128;
         if (jg < 128) jg = 128;
@@ -901,6 +1083,14 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
             p.J = (int)jg;
             p.smem = smem;
             p.ws_bytes = align_up((size_t)B * N * sizeof(float), 256);
+            const size_t npad = (size_t)(N + 127) / 128 * 128;
+            const size_t row_bytes = (size_t)B * N * npad * sizeof(float);
+            if (row_bytes <= ((size_t)512 << 20) && !getenv("FPSG_KNN_NOROWS")) {
+                p.rows = true;
+                p.npad = (int)npad;
+                p.smem = ((size_t)C * jg + jg + (size_t)kRowsWarps * C * kKnnQB) * sizeof(float) + (size_t)kRowsWarps * kSelCap * sizeof(u64);
+                p.ws_bytes += align_up(row_bytes, 256);
+            }
             return p;
         }
     }
@@ -917,6 +1107,13 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
 size_t knn_workspace(int B, int C, int N, int k) {
     if (B <= 0 || C < 1 || N < 1 || k < 1) return 0;
     return make_knn_plan(B, C, N, k).ws_bytes;
+}
+
+static int knn_launch_rows(const float* x, const float* xx, float* rows, int B, int C, int N, int k, const KnnPlan& p, int64_t* idx, cudaStream_t stream) {
+    if (p.smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(knn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    knn_rows_kernel<<<dim3((unsigned)cdiv(N, kRowsWarps * kKnnQB), (unsigned)B), kRowsThreads, p.smem, stream>>>(x, xx, C, N, k, p.J, p.npad, rows, idx);
+    FPSG_CUDA_OK(cudaGetLastError());
+    return FPSG_OK;
 }
 
 static int knn_launch_gemm(const float* x, const float* xx, int B, int C, int N, int k, const KnnPlan& p, int64_t* idx, cudaStream_t stream) {
@@ -982,6 +1179,9 @@ int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx,
         case 1:
             if (getenv("FPSG_KNN_INSERT"))  // tuning override: the shuffle-insertion kernels also serve k <= 32
                 return c3 ? knn_launch_t<1, true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_blocked<1>(x, xx, B, C, N, k, p, idx, stream);
+            if (p.rows)
+                return knn_launch_rows(x, xx, reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)B * N * sizeof(float), 256)), B, C, N, k,
+                                       p, idx, stream);
             if (p.gemm) return knn_launch_gemm(x, xx, B, C, N, k, p, idx, stream);
             return c3 ? knn_launch_bulk<true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_bulk<false>(x, xx, B, C, N, k, p, idx, stream);
         case 2:
