@@ -905,6 +905,7 @@ __device__ __forceinline__ float warp_sort_desc_f32(float v, int lane) {
     return v;
 }
 
+constexpr int kRowsMaxN = 2048;  // one bit per score of a lane in a 64-bit mask
 constexpr int kRowsThreads = 256, kRowsWarps = kRowsThreads / 32;  // two CTAs per SM: one computes while the other loads a tile
 
 __global__ void __launch_bounds__(kRowsThreads, 2)
@@ -952,18 +953,27 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
             for (int q = 0; q < kKnnQB; ++q)
 #pragma unroll
                 for (int t = 0; t < kKnnTC; ++t) dot[q][t] = 0.f;
+            // software-pipelined over channels: the operands of channel c+1 are loaded while channel c is multiplied
+            // (the load past the last channel reads the norms row / the next warp's queries: valid memory, never used)
             const float* tp = sTile + jl;
+            const float* qp = myQ;
+            float4 cv = *reinterpret_cast<const float4*>(tp);
+            float4 qa = *reinterpret_cast<const float4*>(qp), qb = *reinterpret_cast<const float4*>(qp + 4);
 #pragma unroll 2
             for (int c = 0; c < C; ++c) {
-                const float4 cv = *reinterpret_cast<const float4*>(tp + (size_t)c * J);
-                const float4 qa = *reinterpret_cast<const float4*>(myQ + c * kKnnQB);
-                const float4 qb = *reinterpret_cast<const float4*>(myQ + c * kKnnQB + 4);
+                tp += J;
+                qp += kKnnQB;
+                const float4 ncv = *reinterpret_cast<const float4*>(tp);
+                const float4 nqa = *reinterpret_cast<const float4*>(qp), nqb = *reinterpret_cast<const float4*>(qp + 4);
                 const float qv[kKnnQB] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
                 const float cc[kKnnTC] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
                 for (int q = 0; q < kKnnQB; ++q)
 #pragma unroll
                     for (int t = 0; t < kKnnTC; ++t) dot[q][t] = __fmaf_rn(qv[q], cc[t], dot[q][t]);
+                cv = ncv;
+                qa = nqa;
+                qb = nqb;
             }
             const float4 nx = *reinterpret_cast<const float4*>(sXX + jl);
             const float nxx[kKnnTC] = {-nx.x, -nx.y, -nx.z, -nx.w};
@@ -990,21 +1000,31 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
         for (int z = 1; z < kKnnQB; ++z) mine = z == q ? cm[z] : mine;
         const float thr = __shfl_sync(0xffffffffu, warp_sort_desc_f32(mine, lane), k - 1);
         const float* row = myRows + (size_t)q * npad;
-        int cnt = 0;
-        __syncwarp();  // the previous query's keys are no longer read
-        for (int s0 = 0; s0 < npad; s0 += 128) {
+        // this lane's scores >= thr as a bit mask (bit 4*step + t), then positions by a warp prefix sum of the counts
+        u64 mask = 0ull;
+        for (int s0 = 0, bit = 0; s0 < npad; s0 += 128, bit += 4) {  // npad <= 2048 (kRowsMaxN): at most 64 scores per lane
             const float4 p4 = *reinterpret_cast<const float4*>(row + s0);
-            const float p[4] = {p4.x, p4.y, p4.z, p4.w};
+            const int j = s0 + 4 * lane;
+            const unsigned m4 = (j < N && p4.x >= thr ? 1u : 0u) | (j + 1 < N && p4.y >= thr ? 2u : 0u) |
+                                (j + 2 < N && p4.z >= thr ? 4u : 0u) | (j + 3 < N && p4.w >= thr ? 8u : 0u);
+            mask |= (u64)m4 << bit;
+        }
+        const int mine_n = __popcll(mask);
+        int incl = mine_n;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int j = s0 + 4 * lane + t;
-                const bool pass = j < N && p[t] >= thr;
-                const unsigned m = __ballot_sync(0xffffffffu, pass);
-                if (m) {  // warp-uniform
-                    const int pos = cnt + __popc(m & lt_mask);
-                    if (pass && pos < kSelCap) myKey[pos] = knn_key_of(p[t], j);
-                    cnt += __popc(m);
-                }
+        for (int o = 1; o < 32; o <<= 1) {
+            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        const int cnt = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();  // the previous query's keys are no longer read
+        if (cnt <= kSelCap) {
+            int pos = incl - mine_n;
+            while (mask) {
+                const int bit = __ffsll((long long)mask) - 1;
+                mask &= mask - 1;
+                const int off = (bit >> 2) * 128 + 4 * lane + (bit & 3);
+                myKey[pos++] = knn_key_of(row[off - 4 * lane], off);
             }
         }
         __syncwarp();
@@ -1085,7 +1105,7 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
             p.ws_bytes = align_up((size_t)B * N * sizeof(float), 256);
             const size_t npad = (size_t)(N + 127) / 128 * 128;
             const size_t row_bytes = (size_t)B * N * npad * sizeof(float);
-            if (row_bytes <= ((size_t)512 << 20) && !getenv("FPSG_KNN_NOROWS")) {
+            if (N <= kRowsMaxN && row_bytes <= ((size_t)512 << 20) && !getenv("FPSG_KNN_NOROWS")) {
                 p.rows = true;
                 p.npad = (int)npad;
                 p.smem = ((size_t)C * jg + jg + (size_t)kRowsWarps * C * kKnnQB) * sizeof(float) + (size_t)kRowsWarps * kSelCap * sizeof(u64);
