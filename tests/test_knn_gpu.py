@@ -53,6 +53,22 @@ def test_knn_duplicates_and_ties():
     assert (got == O.knn_f32(x.numpy(), 20)).all()
 
 
+@pytest.mark.parametrize("C,N,k", [(3, 300, 20), (3, 1500, 32), (16, 300, 20), (64, 700, 7), (3, 2500, 20), (8, 2048, 32)])
+def test_knn_degenerate_clouds_take_the_overflow_paths(C, N, k):
+    """All points identical / a handful of distinct points: every candidate ties with the threshold, so the
+    threshold-selection kernels must fall back to their streaming merge -- and still be bit-exact (lowest index
+    first among equal values)."""
+    import fpsg_b200
+    O = _oracle()
+    g = torch.Generator().manual_seed(N + C)
+    same = torch.randn(1, C, 1, generator=g).expand(1, C, N).contiguous()
+    few = torch.randn(1, C, 3, generator=g)[:, :, torch.randint(0, 3, (N,), generator=g)].contiguous()
+    for x in (same, few):
+        got = fpsg_b200.knn(x.cuda(), k).cpu().numpy()
+        ref = O.knn_f32(x.numpy(), k)
+        assert (got == ref).all(), f"{(got != ref).sum()} of {ref.size} positions differ"
+
+
 def test_knn_vs_torch_reference_formula_on_gpu():
     """Same-device check against the reference expression (src/dgcnn/model.py:13-20) evaluated by torch on the
     GPU: neighbour values must agree to FP32 rounding of the expanded form."""
