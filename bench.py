@@ -40,8 +40,8 @@ B_PER_GPU, N_PTS, M_PTS = 32, 2048, 2048
 WORKLOAD = "c1: Chamfer loss fwd+bwd(p1), B=32 per GPU, N=M=2048, synthetic xyz float32"
 METRIC = "chamfer_fwd_bwd_pairs_per_s"
 RING_SETS = 96  # distinct input batches cycled through: 96 x 1.57 MB = 151 MB > 126 MB L2
-# dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch (profiles/r01_chamfer_kernels_raw.csv, r01_summary.md)
-SWEEP_DRAM_TRAFFIC_BYTES = 1.597e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch (profiles/r01b_chamfer_kernels_raw.csv, r01_summary.md)
+SWEEP_DRAM_TRAFFIC_BYTES = 1.599e6
 
 
 def make_inputs(batch, n, m, seed, device=None, pin=False):
