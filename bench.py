@@ -208,7 +208,20 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout when the communicator is created (first collective); stdout must
+        # carry exactly one JSON line, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     from fpsg_b200 import _lib
     import fpsg_b200
@@ -230,7 +243,7 @@ def main():
     loss = torch.empty(B, device=dev)
     gloss = torch.ones(B, device=dev)
     gp1 = torch.empty(B, N, 3, device=dev)
-    totals = [torch.zeros((), device=dev), torch.zeros((), device=dev)]
+    totals = [torch.zeros(2, device=dev), torch.zeros(2, device=dev)]  # [sum over the local pairs, the same per segment]
     pending = [None, None]
     nbytes = L.fpsg_chamfer_fwd_workspace_bytes(B, N, M)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -239,21 +252,32 @@ def main():
     ptrs = [(a.data_ptr(), b.data_ptr()) for a, b in ring]
     o = (loss.data_ptr(), dist1.data_ptr(), dist2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), ws.data_ptr(), gloss.data_ptr(), gp1.data_ptr())
 
+    # N > 1: the local sum of the per-pair losses comes out of the finalize kernel itself (the one-segment form of
+    # fpsg_chamfer_multi_loss_fwd), so no reduction kernel sits between the forward and the backward
+    segs = []
+    for a_, b_ in ptrs:
+        sg = (_lib.ChamferSegment * 1)()
+        sg[0].p1, sg[0].p2, sg[0].gp1, sg[0].gp2, sg[0].batch, sg[0].weight = a_, b_, None, None, B, 1.0
+        segs.append(sg)
+    tot_ptrs = [t.data_ptr() for t in totals]
+    tot_views = [t[:1] for t in totals]
+
     def step(i):
         a, b = ptrs[i % RING_SETS]
-        _lib.check(L.fpsg_chamfer_loss_fwd(a, b, B, N, M, 1.0, 1.0, o[0], o[1], o[2], o[3], o[4], o[5], nbytes, sp))
-        if world > 1:
+        if world == 1:
+            _lib.check(L.fpsg_chamfer_loss_fwd(a, b, B, N, M, 1.0, 1.0, o[0], o[1], o[2], o[3], o[4], o[5], nbytes, sp))
+        else:
             # the scalar the reference logs: all-reduced asynchronously, consumed one step later, so the
             # collective's latency overlaps the backward and the next forward instead of stalling the stream
             k = i & 1
-            torch.sum(loss, dim=0, out=totals[k])
-            pending[k] = dist.all_reduce(totals[k], op=dist.ReduceOp.SUM, async_op=True)
+            _lib.check(L.fpsg_chamfer_multi_loss_fwd(segs[i % RING_SETS], 1, N, M, 1.0, 1.0, o[0], tot_ptrs[k], o[3], o[4], o[5], nbytes, sp))
+            pending[k] = dist.all_reduce(tot_views[k], op=dist.ReduceOp.SUM, async_op=True)
         _lib.check(L.fpsg_chamfer_loss_bwd(a, b, o[3], o[4], o[6], 1.0, 1.0, B, N, M, o[7], None, None, 0, sp))
         if world > 1 and pending[(i + 1) & 1] is not None:
             pending[(i + 1) & 1].wait()
             pending[(i + 1) & 1] = None
 
-    kernels_per_step = 3  # sweep, finalize (+ fused loss), backward (the NCCL / torch.sum kernels for N > 1 are not ours)
+    kernels_per_step = 3  # sweep, finalize (+ fused loss and batch sum), backward (the NCCL kernel for N > 1 is not ours)
 
     def barrier():
         if world > 1:
