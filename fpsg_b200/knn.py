@@ -6,7 +6,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .chamfer import _stream_ptr
+from .chamfer import _device_guard, _stream_ptr
 
 
 def knn(x: torch.Tensor, k: int) -> torch.Tensor:
@@ -30,7 +30,7 @@ def knn(x: torch.Tensor, k: int) -> torch.Tensor:
     if B == 0:
         return idx
     L = _lib.lib()
-    with torch.cuda.device(x.device):
+    with _device_guard(x.device):
         nbytes = L.fpsg_knn_workspace_bytes(B, C, N, k)
         ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=x.device)
         rc = L.fpsg_knn_fwd(x.data_ptr(), B, C, N, k, idx.data_ptr(), ws.data_ptr(), nbytes,
