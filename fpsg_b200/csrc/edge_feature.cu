@@ -9,9 +9,13 @@
 // and the backward gathers through an inverted index of idx (built once per call with integer atomics, shared by all
 // channels) instead of scattering with floating-point atomics:
 //     gx[b,c,n] = sum_j (g[b,C+c,n,j] - g[b,c,n,j]) + sum_{(n',j): idx[b,n',j] = n} g[b,c,n',j]      (double accumulation)
-// The forward is HBM-write-bound (8*C*N*k bytes per cloud); the backward reads as much but is bound by the random
-// gathers (one L1 wavefront per gathered element) -- shared-memory staging of the plane and shared-memory double
-// atomics were both tried in round 1 and were slower (uncoalesced list reads; 64-bit CAS loops).
+// The forward is HBM-write-bound (8*C*N*k bytes per cloud). The backward reads as much. Gathering straight from
+// global memory costs one 32-byte sector per 4-byte element, so when a (cloud, channel) plane of the difference half
+// (N*k floats) fits shared memory twice, a persistent grid (one 1024-thread CTA per SM) streams the planes through a
+// double buffer with 16-byte cp.async -- the next plane arrives while the current one is gathered -- with the cloud's
+// inverted index held in shared memory as 16-bit slot numbers. Larger planes use the direct global gather.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fpsg {
@@ -149,6 +153,139 @@ edge_feature_bwd_kernel(const float* __restrict__ g, const int* __restrict__ sta
     gx[((size_t)b * C + c) * N + n] = (float)acc;
 }
 
+// Plane-staged backward: CTA g owns the planes [g*P/G, (g+1)*P/G) of the flattened (cloud, channel) range.
+constexpr int kPlaneThreads = 1024;
+constexpr int kPlaneK4 = 5;  // k <= 20 on this path (DGCNN uses 20)
+constexpr int kHubCap = 32;  // bucket entries a point's own thread gathers; the rest of a longer bucket ("hub" point: kNN graphs
+                             // of high-dimensional features have a few points with hundreds of in-edges) is summed by a whole warp
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+__global__ void __launch_bounds__(kPlaneThreads, 1)
+edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict__ start_all, const int* __restrict__ list_all, int B, int C,
+                              int N, int k, float* __restrict__ gx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nk = N * k;
+    float* sPlane = reinterpret_cast<float*>(smem_raw);                          // [2][nk] difference-half planes
+    int* sStart = reinterpret_cast<int*>(sPlane + 2 * (size_t)nk);                // [N + 1]
+    unsigned short* sList = reinterpret_cast<unsigned short*>(sStart + N + 1);    // [nk] slots, grouped by target point
+    __shared__ unsigned short sHub[kPlaneThreads];  // hub points of the current cloud
+    __shared__ double sHubAcc[kPlaneThreads];       // their partial sums between the two phases
+    __shared__ int sNHub;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int myslot = -1;  // this thread's point is hub number myslot of the current cloud
+    const long long planes = (long long)B * C;
+    const int p0 = (int)(planes * blockIdx.x / gridDim.x), p1 = (int)(planes * (blockIdx.x + 1) / gridDim.x);
+
+    auto prefetch = [&](int p, int buf) {
+        const int b = p / C, c = p - b * C;
+        const float4* src = reinterpret_cast<const float4*>(g + ((size_t)b * 2 * C + c) * nk);
+        float4* dst = reinterpret_cast<float4*>(sPlane + (size_t)buf * nk);
+        for (int q = tid; q < (nk >> 2); q += kPlaneThreads) cp_async16(dst + q, src + q);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // The centre half is read exactly once and only its per-point sum is needed: a thread loads the k values of its
+    // point (N <= 1024: one point per thread) for the NEXT plane at the top of an iteration and folds them into one
+    // double at the end of it, so their HBM latency hides behind the current plane's gathers.
+    const int k4 = k >> 2;
+    float4 mreg[kPlaneK4];
+    auto load_centre = [&](int p) {
+        const int b = p / C, c = p - b * C;
+        const float4* gm4 = reinterpret_cast<const float4*>(g + ((size_t)b * 2 * C + C + c) * nk + (size_t)min(tid, N - 1) * k);
+#pragma unroll
+        for (int j = 0; j < kPlaneK4; ++j)
+            if (j < k4) mreg[j] = __ldcs(gm4 + j);
+    };
+    auto fold_centre = [&]() {
+        double s_ = 0.0;
+#pragma unroll
+        for (int j = 0; j < kPlaneK4; ++j)
+            if (j < k4) s_ += ((double)mreg[j].x + (double)mreg[j].y) + ((double)mreg[j].z + (double)mreg[j].w);
+        return s_;
+    };
+    double msum = 0.0;
+
+    int cur_b = -1;
+    if (p0 < p1) {
+        prefetch(p0, 0);
+        load_centre(p0);
+        msum = fold_centre();
+    }
+    for (int p = p0; p < p1; ++p) {
+        const int b = p / C, c = p - b * C;
+        const int buf = (p - p0) & 1;
+        if (p + 1 < p1) prefetch(p + 1, buf ^ 1);
+        if (b != cur_b) {  // CTA-uniform: the inverted index of a new cloud (the previous plane's readers passed the barrier below)
+            cur_b = b;
+            const int* __restrict__ start = start_all + (size_t)b * (N + 1);
+            const int* __restrict__ list = list_all + (size_t)b * nk;
+            for (int n = tid; n <= N; n += kPlaneThreads) sStart[n] = __ldg(start + n);
+            for (int e = tid; e < nk; e += kPlaneThreads) sList[e] = (unsigned short)__ldg(list + e);
+            if (tid == 0) sNHub = 0;
+            __syncthreads();
+            myslot = -1;
+            if (tid < N && __ldg(start + tid + 1) - __ldg(start + tid) > kHubCap) {
+                myslot = atomicAdd(&sNHub, 1);
+                sHub[myslot] = (unsigned short)tid;
+            }
+        }
+        if (p + 1 < p1)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // plane p and the index are in shared memory for everyone
+
+        const float* __restrict__ plane = sPlane + (size_t)buf * nk;
+        if (p + 1 < p1) load_centre(p + 1);  // consumed by fold_centre() below, after this plane's gathers
+        if (tid < N) {
+            const int n = tid;
+            double acc = msum;
+            const float4* gd4 = reinterpret_cast<const float4*>(plane + n * k);
+#pragma unroll
+            for (int j = 0; j < kPlaneK4; ++j) {
+                if (j < k4) {
+                    const float4 d = gd4[j];
+                    acc -= ((double)d.x + (double)d.y) + ((double)d.z + (double)d.w);
+                }
+            }
+            const int s0 = sStart[n], s1 = min(sStart[n + 1], s0 + kHubCap);
+            for (int s_ = s0; s_ < s1; s_ += 4) {
+                float v[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[t] = s_ + t < s1 ? plane[sList[s_ + t]] : 0.f;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc += (double)v[t];
+            }
+            if (myslot < 0)
+                gx[((size_t)b * C + c) * N + n] = (float)acc;
+            else
+                sHubAcc[myslot] = acc;
+        }
+        __syncthreads();
+        // the long tails of the hub points' buckets, a warp per hub
+        for (int h = w; h < sNHub; h += kPlaneThreads / 32) {
+            const int n = sHub[h];
+            const int s1 = sStart[n + 1];
+            double part = 0.0;
+            for (int s_ = sStart[n] + kHubCap + lane; s_ < s1; s_ += 32) part += (double)plane[sList[s_]];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+            if (lane == 0) gx[((size_t)b * C + c) * N + n] = (float)(sHubAcc[h] + part);
+        }
+        if (p + 1 < p1) msum = fold_centre();
+        __syncthreads();  // everyone is done with this buffer before the prefetch after next overwrites it
+    }
+}
+
+static size_t edge_plane_smem(int N, int k) {
+    const size_t nk = (size_t)N * k;
+    return 2 * nk * sizeof(float) + (size_t)(N + 1) * sizeof(int) + nk * sizeof(unsigned short);
+}
+
 int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out, cudaStream_t stream) {
     if (B < 0 || C < 1 || N < 1 || k < 1) return fail(FPSG_EINVAL, "edge_feature: need B >= 0, C, N, k >= 1 (got B=%d C=%d N=%d k=%d)", B, C, N, k);
     if (B == 0) return FPSG_OK;
@@ -190,6 +327,18 @@ int edge_feature_backward_launch(const float* g, const int64_t* idx, int B, int 
     if (smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(edge_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     edge_invert_kernel<<<B, 1024, smem, stream>>>(idx, N, k, start, list);
     FPSG_CUDA_OK(cudaGetLastError());
+    const long long nk = (long long)N * k;
+    const size_t psmem = edge_plane_smem(N, k);
+    if (nk <= 65535 && (k & 3) == 0 && k <= 4 * kPlaneK4 && N <= kPlaneThreads && psmem <= 212 * 1024 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && !getenv("FPSG_EDGE_NOPLANE")) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long planes = (long long)B * C;
+        const unsigned grid = (unsigned)(planes < sms ? planes : sms);
+        FPSG_CUDA_OK(cudaFuncSetAttribute(edge_feature_bwd_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        edge_feature_bwd_plane_kernel<<<grid, kPlaneThreads, psmem, stream>>>(g, start, list, B, C, N, k, gx);
+        FPSG_CUDA_OK(cudaGetLastError());
+        return FPSG_OK;
+    }
     const dim3 grid((unsigned)cdiv(N, kEdgeThreads), (unsigned)C, (unsigned)B);
     edge_feature_bwd_kernel<<<grid, kEdgeThreads, 0, stream>>>(g, start, list, C, N, k, gx);
     FPSG_CUDA_OK(cudaGetLastError());

@@ -918,7 +918,6 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
     u64* sKey = reinterpret_cast<u64*>(sQ + (size_t)kRowsWarps * C * kKnnQB);  // [kRowsWarps][64]
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int b = blockIdx.y;
     const int i0 = (blockIdx.x * kRowsWarps + w) * kKnnQB;
     const float* __restrict__ xb = x + (size_t)b * C * N;
@@ -1058,16 +1057,6 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
         }
         if (lane < k) idx[((size_t)b * N + i0 + q) * k + lane] = (int64_t)(0xffffffffu - (unsigned)key);
     }
-}
-
-static int sm_count_knn() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
-        else return 148;
-    }
-    return n;
 }
 
 struct KnnPlan {
