@@ -1063,6 +1063,7 @@ struct KnnPlan {
     int KR;
     bool rows;   // generic C, k <= 32: knn_rows_kernel (scores streamed to scratch rows in the workspace)
     int npad;    // floats per scratch row
+    int chunk;   // clouds per launch of knn_rows_kernel: the scratch (chunk * N rows) is reused by the next launch
     bool gemm;  // generic C, k <= 32: the register-tiled scoring kernel
     int J;
     size_t smem;
@@ -1081,6 +1082,7 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
     p.gemm = false;
     p.rows = false;
     p.npad = 0;
+    p.chunk = 0;
     if (p.KR == 1 && C != 3 && !getenv("FPSG_KNN_INSERT") && !getenv("FPSG_KNN_NOGEMM")) {
         long long jg = (long long)(kKnnTileBytes / sizeof(float)) / (C + 1) / 128 * 128;
         if (jg < 128) jg = 128;
@@ -1093,10 +1095,17 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
             p.smem = smem;
             p.ws_bytes = align_up((size_t)B * N * sizeof(float), 256);
             const size_t npad = (size_t)(N + 127) / 128 * 128;
-            const size_t row_bytes = (size_t)B * N * npad * sizeof(float);
-            if (N <= kRowsMaxN && row_bytes <= ((size_t)512 << 20) && !getenv("FPSG_KNN_NOROWS")) {
+            // scratch rows for at most ~256 MB worth of clouds at a time (at least one cloud): launches on the same stream
+            // run back to back, so the next chunk can reuse the rows of the previous one
+            const size_t cloud_bytes = (size_t)N * npad * sizeof(float);
+            size_t chunk = ((size_t)256 << 20) / cloud_bytes;
+            if (chunk < 1) chunk = 1;
+            if (chunk > (size_t)B) chunk = (size_t)B;
+            const size_t row_bytes = chunk * cloud_bytes;
+            if (N <= kRowsMaxN && !getenv("FPSG_KNN_NOROWS")) {
                 p.rows = true;
                 p.npad = (int)npad;
+                p.chunk = (int)chunk;
                 p.smem = ((size_t)C * jg + jg + (size_t)kRowsWarps * C * kKnnQB) * sizeof(float) + (size_t)kRowsWarps * kSelCap * sizeof(u64);
                 p.ws_bytes += align_up(row_bytes, 256);
             }
@@ -1120,8 +1129,12 @@ size_t knn_workspace(int B, int C, int N, int k) {
 
 static int knn_launch_rows(const float* x, const float* xx, float* rows, int B, int C, int N, int k, const KnnPlan& p, int64_t* idx, cudaStream_t stream) {
     if (p.smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(knn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    knn_rows_kernel<<<dim3((unsigned)cdiv(N, kRowsWarps * kKnnQB), (unsigned)B), kRowsThreads, p.smem, stream>>>(x, xx, C, N, k, p.J, p.npad, rows, idx);
-    FPSG_CUDA_OK(cudaGetLastError());
+    for (int b0 = 0; b0 < B; b0 += p.chunk) {
+        const int nb = min(p.chunk, B - b0);
+        knn_rows_kernel<<<dim3((unsigned)cdiv(N, kRowsWarps * kKnnQB), (unsigned)nb), kRowsThreads, p.smem, stream>>>(
+            x + (size_t)b0 * C * N, xx + (size_t)b0 * N, C, N, k, p.J, p.npad, rows, idx + (size_t)b0 * N * k);
+        FPSG_CUDA_OK(cudaGetLastError());
+    }
     return FPSG_OK;
 }
 

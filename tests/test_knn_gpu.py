@@ -32,7 +32,7 @@ def test_knn_matches_reference_golden(path):
 @pytest.mark.parametrize("B,C,N,k", [(2, 3, 100, 20), (3, 3, 1024, 20), (2, 3, 1000, 1), (1, 3, 33, 33), (2, 3, 257, 64),
                                      (1, 3, 300, 128), (2, 64, 300, 20), (2, 64, 1024, 20), (1, 128, 520, 20),
                                      (2, 5, 77, 7), (1, 3, 9000, 20), (1, 70, 100, 40), (1, 16, 150, 100), (1, 400, 64, 5),
-                                     (1, 64, 2100, 20), (2, 1, 50, 3)])
+                                     (1, 64, 2100, 20), (2, 1, 50, 3), (40, 8, 2048, 20)])
 def test_knn_bit_exact_vs_oracle(B, C, N, k):
     import fpsg_b200
     O = _oracle()
