@@ -621,14 +621,12 @@ knn_gemm_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
 constexpr int kSelS = 4;                        // warps that share 32 queries in pass 1
 constexpr int kSelThreads = 256;
 constexpr int kSelQ = kSelThreads / kSelS;      // queries per CTA
-constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kSelGroups = 32;                  // coarse groups (>= k)
 constexpr int kSelFine = 128;                   // most fine groups per cloud
 constexpr int kSelFmStride = kSelFine + 1;      // floats per query row of the fine maxima (conflict-free both ways)
-constexpr int kSelFgStride = kSelFine + 4;      // bytes per list of fine groups to re-score (+ the sentinel)
-constexpr int kSelCap = 64;                     // candidate keys per query
+constexpr int kSelCap = 64;                     // candidates per query (and per thread column)
+constexpr int kSelListStride = kSelCap + 2;     // u16 elements per query row of the candidate lists
 constexpr int kSelMaxN = 8192;                  // the cloud must fit shared memory as float4
-static_assert(kSelWarps * 2 * kSelCap * sizeof(unsigned long long) >= kSelGroups * kSelQ * sizeof(float), "key scratch holds the sorted group maxima");
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
@@ -672,14 +670,19 @@ struct KnnSelPlan {
     int npad;    // nfine << fsh
     size_t smem;
 };
+constexpr size_t kSelRegionA = (size_t)kSelQ * kSelFmStride * sizeof(float);  // fine maxima, later the candidate columns
+constexpr size_t kSelRegionB = (size_t)kSelQ * kSelListStride * sizeof(unsigned short);  // threshold scratch, group lists, query lists
+static_assert(kSelRegionA >= (size_t)kSelCap * kSelThreads * sizeof(unsigned short), "candidate columns fit the fine-maxima region");
+static_assert(kSelRegionB >= (size_t)kSelGroups * kSelQ * sizeof(float) && kSelRegionB >= (size_t)(kSelFine / kSelS) * kSelThreads,
+              "region B holds the sorted group maxima and the per-thread group lists");
 static KnnSelPlan knn_select_plan(int N) {
     KnnSelPlan p;
     p.fsh = 3;
     while (((long long)kSelFine << p.fsh) < N) ++p.fsh;
     p.nfine = (N + (1 << p.fsh) - 1) >> p.fsh;
     p.npad = p.nfine << p.fsh;
-    p.smem = (size_t)(p.npad + (1 << p.fsh)) * sizeof(float4) + (size_t)kSelQ * kSelFmStride * sizeof(float) + (size_t)kSelQ * sizeof(float) +
-             (size_t)kSelWarps * 2 * kSelCap * sizeof(u64) + (size_t)kSelWarps * 2 * kSelFgStride;
+    p.smem = (size_t)(p.npad + (1 << p.fsh)) * sizeof(float4) + kSelRegionA + kSelRegionB + (size_t)kSelQ * sizeof(float) +
+             (size_t)kSelThreads * sizeof(int) + (size_t)kSelQ * sizeof(int);
     return p;
 }
 
@@ -687,12 +690,18 @@ __global__ void __launch_bounds__(kSelThreads)
 knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh, int64_t* __restrict__ idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int npad = nfine << fsh;
-    const int ntile = npad + (1 << fsh);  // one more fine group, all padding: the target of out-of-range lanes
-    float4* sTile = reinterpret_cast<float4*>(smem_raw);                            // [ntile] (x, y, z, -xx)
-    float* sFm = reinterpret_cast<float*>(sTile + ntile);                           // [Q][129] fine group maxima
-    float* sThr = sFm + kSelQ * kSelFmStride;                                       // [Q]
-    u64* sKey = reinterpret_cast<u64*>(sThr + kSelQ);                               // [warps][2][cap] candidate keys
-    unsigned char* sFG = reinterpret_cast<unsigned char*>(sKey + kSelWarps * 2 * kSelCap);  // [warps][2][128] fine groups to re-score
+    const int ntile = npad + (1 << fsh);  // one more fine group, all padding: where idle lanes point
+    float4* sTile = reinterpret_cast<float4*>(smem_raw);                              // [ntile] (x, y, z, -xx)
+    unsigned char* regA = reinterpret_cast<unsigned char*>(sTile + ntile);
+    unsigned char* regB = regA + kSelRegionA;
+    float* sFm = reinterpret_cast<float*>(regA);                                      // [Q][129] fine group maxima ...
+    unsigned short* sBuf = reinterpret_cast<unsigned short*>(regA);                   // ... then [cap][T] candidate columns
+    float* sScr = reinterpret_cast<float*>(regB);                                     // [32][Q] sorted coarse maxima ...
+    unsigned char* sGl = regB;                                                        // ... then [32][T] fine groups to re-score ...
+    unsigned short* sList = reinterpret_cast<unsigned short*>(regB);                  // ... then [Q][66] candidates of a query
+    float* sThr = reinterpret_cast<float*>(regB + kSelRegionB);                       // [Q]
+    int* sCntP = reinterpret_cast<int*>(sThr + kSelQ);                                // [T] candidates found by a thread, -1 = overflow
+    int* sCnt = sCntP + kSelThreads;                                                  // [Q] candidates of a query, -1 = overflow
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int wq = w / kSelS, part = w - wq * kSelS;  // warps wq*4 .. wq*4+3 share 32 queries
@@ -713,13 +722,14 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     }
     __syncthreads();
 
+    const int i = blockIdx.x * kSelQ + ql;
+    const float4 q = sTile[min(i, N - 1)];  // rows past N are clamped: computed, never written
+    const float xxi = -q.w;
+    const int f0 = (part * nfine) / kSelS, f1 = ((part + 1) * nfine) / kSelS;  // this thread's share of the fine groups
+    const int octs = 1 << (fsh - 3);
+
     // ---- pass 1: maxima of this warp's quarter of the fine groups, one query per thread ----
     {
-        const int i = blockIdx.x * kSelQ + ql;
-        const float4 q = sTile[min(i, N - 1)];  // rows past N are clamped: computed, never used
-        const float xxi = -q.w;
-        const int f0 = (part * nfine) / kSelS, f1 = ((part + 1) * nfine) / kSelS;
-        const int octs = 1 << (fsh - 3);
         float* fm = sFm + ql * kSelFmStride;
         if (fsh == 3) {  // one octet per fine group (N <= 1024): no inner loop
 #pragma unroll 2
@@ -778,78 +788,123 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
                 }
             }
         }
-        // v[k-1] without dynamic register indexing: through shared memory (the key scratch is idle until the barrier)
-        float* scr = reinterpret_cast<float*>(sKey);  // [32][Q] floats = exactly the key scratch
+        // v[k-1] without dynamic register indexing: through shared memory
 #pragma unroll
-        for (int c = 0; c < kSelGroups; ++c) scr[c * kSelQ + ql] = v[c];
-        sThr[ql] = scr[(k - 1) * kSelQ + ql];
+        for (int c = 0; c < kSelGroups; ++c) sScr[c * kSelQ + ql] = v[c];
+        sThr[ql] = sScr[(k - 1) * kSelQ + ql];
+    }
+    __syncthreads();
+    const float thr = sThr[ql];
+
+    // ---- this thread's fine groups whose maximum reaches the threshold: a private list (branch-free append) ----
+    int ngl = 0;
+    {
+        const float* fm = sFm + ql * kSelFmStride;
+        unsigned char* gl = sGl + tid;
+        for (int f = f0; f < f1; ++f) {
+            gl[ngl * kSelThreads] = (unsigned char)f;
+            ngl += fm[f] >= thr ? 1 : 0;
+        }
+    }
+    __syncthreads();  // every read of the fine maxima is done: their region becomes the candidate columns
+
+    // ---- re-score the listed groups: indices of the candidates with pd >= thr go to this thread's column ----
+    {
+        int wmax = ngl;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        const unsigned col = static_cast<unsigned>(__cvta_generic_to_shared(sBuf + tid));
+        const unsigned stepb = 2u * kSelThreads;
+        const unsigned limit = col + (kSelCap - 8) * stepb;
+        unsigned p = col;
+        bool ovf = false;
+#pragma unroll 1
+        for (int g = 0; g < wmax; ++g) {
+            const int f = g < ngl ? (int)sGl[g * kSelThreads + tid] : nfine;  // idle lanes score the all-padding group
+            const int j0 = f << fsh;
+#pragma unroll 1
+            for (int o = 0; o < octs; ++o) {
+                // fine groups start on 128-byte boundaries, so lanes reading "their" candidate u of different groups would
+                // all hit the same four banks: every lane walks its octet rotated by its lane number instead
+                const float4* tp = sTile + j0 + 8 * o;
+                float pd[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) pd[u] = knn_pd3(q, xxi, tp[(u + lane) & 7]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned short jv = (unsigned short)(j0 + 8 * o + ((u + lane) & 7));
+                    asm volatile(
+                        "{\n\t.reg .pred pp;\n\t"
+                        "st.shared.u16 [%0], %1;\n\t"
+                        "setp.ge.f32 pp, %2, %3;\n\t"
+                        "@pp add.u32 %0, %0, %4;\n\t}"
+                        : "+r"(p)
+                        : "h"(jv), "f"(pd[u]), "f"(thr), "r"(stepb)
+                        : "memory");
+                }
+                if (p > limit) {
+                    ovf = true;
+                    p = limit;
+                }
+            }
+        }
+        sCntP[tid] = ovf ? -1 : (int)((p - col) / stepb);
     }
     __syncthreads();
 
-    // ---- final: a warp per query, two queries at a time ----
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int cmask = (1 << fsh) - 1;
-    u64* myKey = sKey + (size_t)w * 2 * kSelCap;
-    unsigned char* myFG = sFG + (size_t)w * 2 * kSelFgStride;
+    // ---- the four shares of a query, concatenated into its row of sList ----
+    {
+        int before = 0, total = 0;
+        bool ovf = false;
+#pragma unroll
+        for (int pp = 0; pp < kSelS; ++pp) {
+            const int c = sCntP[(wq * kSelS + pp) * 32 + lane];
+            ovf |= c < 0;
+            if (pp < part) before += c;
+            total += c;
+        }
+        ovf |= total > kSelCap;
+        if (!ovf) {
+            const int mine = sCntP[tid];
+            for (int e = 0; e < mine; ++e) sList[ql * kSelListStride + before + e] = sBuf[e * kSelThreads + tid];
+        }
+        if (part == 0) sCnt[ql] = ovf ? -1 : total;
+    }
+    __syncthreads();
+
+    // ---- final: a warp sorts the candidates of its queries, two queries at a time, and writes the first k ----
 #pragma unroll 1
     for (int n = 0; n < 32 / kSelS; n += 2) {
-        int tq[2], iq[2], ng[2], cnt[2];
-        float thr[2];
+        int tq[2], iq[2], c[2];
         float4 qp[2];
+        u64 key[2];
 #pragma unroll
         for (int z = 0; z < 2; ++z) {
             tq[z] = wq * 32 + part + (n + z) * kSelS;
             iq[z] = blockIdx.x * kSelQ + tq[z];
             if (iq[z] >= N) iq[z] = -1;  // warp-uniform
+            c[z] = iq[z] >= 0 ? sCnt[tq[z]] : 0;
             qp[z] = sTile[max(iq[z], 0)];
-            thr[z] = sThr[tq[z]];
-            ng[z] = 0;
-            cnt[z] = 0;
+            key[z] = 0ull;
         }
-        __syncwarp();  // the previous pair's scratch is no longer read
-        // fine groups whose maximum reaches the threshold
 #pragma unroll 1
-        for (int f = lane; f < kSelFine; f += 32) {
-#pragma unroll
-            for (int z = 0; z < 2; ++z) {
-                const bool qual = iq[z] >= 0 && f < nfine && sFm[tq[z] * kSelFmStride + f] >= thr[z];
-                const unsigned m = __ballot_sync(0xffffffffu, qual);
-                if (qual) myFG[z * kSelFgStride + ng[z] + __popc(m & lt_mask)] = (unsigned char)f;
-                ng[z] += __popc(m);
-            }
-        }
-        if (lane < 2) myFG[lane * kSelFgStride + ng[lane]] = (unsigned char)nfine;  // sentinel: the all-padding group
-        __syncwarp();
-        // re-score their candidates, keep the keys of those with pd >= threshold
-        const int tot0 = ng[0] << fsh, tot1 = ng[1] << fsh;
-#pragma unroll 1
-        for (int c0 = 0; c0 < max(tot0, tot1); c0 += 32) {
-            const int c = c0 + lane;
-#pragma unroll
-            for (int z = 0; z < 2; ++z) {
-                const int j = ((int)myFG[z * kSelFgStride + min(c >> fsh, ng[z])] << fsh) + (c & cmask);  // past the list: padding
-                const float pd = knn_pd3(qp[z], -qp[z].w, sTile[j]);
-                const bool pass = pd >= thr[z];
-                const unsigned m = __ballot_sync(0xffffffffu, pass);
-                const int pos = cnt[z] + __popc(m & lt_mask);
-                if (pass && pos < kSelCap) myKey[z * kSelCap + pos] = knn_key_of(pd, j);
-                cnt[z] += __popc(m);
-            }
-        }
-        __syncwarp();
-        // sort (<= 64 keys per query: one or two rounds of 32)
-        u64 key[2] = {0ull, 0ull};
-        const int c0n = cnt[0] <= kSelCap ? cnt[0] : 0, c1n = cnt[1] <= kSelCap ? cnt[1] : 0;
-#pragma unroll 1
-        for (int h = 0; h * 32 < max(c0n, c1n); ++h) {
+        for (int h = 0; h * 32 < max(c[0], c[1]); ++h) {
             const int e = h * 32 + lane;
-            u64 ka = e < c0n ? myKey[e] : 0ull, kb = e < c1n ? myKey[kSelCap + e] : 0ull;
-            warp_sort_desc2(ka, kb, lane);
+            u64 kb[2];
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                kb[z] = 0ull;
+                if (e < c[z]) {
+                    const int j = sList[tq[z] * kSelListStride + e];
+                    kb[z] = knn_key_of(knn_pd3(qp[z], -qp[z].w, sTile[j]), j);
+                }
+            }
+            warp_sort_desc2(kb[0], kb[1], lane);
             if (h == 0) {
-                key[0] = ka;
-                key[1] = kb;
+                key[0] = kb[0];
+                key[1] = kb[1];
             } else {
-                const u64 r0 = __shfl_sync(0xffffffffu, ka, 31 - lane), r1 = __shfl_sync(0xffffffffu, kb, 31 - lane);
+                const u64 r0 = __shfl_sync(0xffffffffu, kb[0], 31 - lane), r1 = __shfl_sync(0xffffffffu, kb[1], 31 - lane);
                 key[0] = key[0] > r0 ? key[0] : r0;
                 key[1] = key[1] > r1 ? key[1] : r1;
                 warp_merge_desc2(key[0], key[1], lane);
@@ -858,7 +913,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
 #pragma unroll
         for (int z = 0; z < 2; ++z) {
             if (iq[z] < 0) continue;  // warp-uniform
-            if (cnt[z] > kSelCap) {
+            if (c[z] < 0) {
                 // more than 64 candidates tie with the threshold: streaming sort-and-merge over the whole cloud
                 u64 kk = 0ull, tau = 0ull;
                 for (int j0 = 0; j0 < N; j0 += 32) {
