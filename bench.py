@@ -353,20 +353,25 @@ def main():
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     cur = torch.cuda.current_stream(dev)
 
+    # N > 1: the global sum of the loss is a logged value only (the backward does not need it), so its all-reduce is
+    # issued asynchronously right after the forward and consumed two steps later -- ranks never wait for each other
+    # inside a step; what every step reads back and synchronises on is its own loss.
+    red = [torch.zeros((), device=dev), torch.zeros((), device=dev)]
+    red_work = [None, None]
+
     def e2e_step(i):
         with torch.no_grad():
             dbuf.copy_(host[i % len(host)], non_blocking=True)
         p1_leaf.grad = None
         val = shim_chamfer(p1_leaf, p2_view).sum()
         if world > 1:
-            red = val.detach().clone()
-            work = dist.all_reduce(red, op=dist.ReduceOp.SUM, async_op=True)
+            kk = i & 1
+            if red_work[kk] is not None:
+                red_work[kk].wait()
+            red[kk].copy_(val.detach())
+            red_work[kk] = dist.all_reduce(red[kk], op=dist.ReduceOp.SUM, async_op=True)
         val.backward()
-        if world > 1:
-            work.wait()
-            loss_host.copy_(red, non_blocking=True)
-        else:
-            loss_host.copy_(val.detach(), non_blocking=True)
+        loss_host.copy_(val.detach(), non_blocking=True)
         cur.synchronize()  # the step's result (and its gradient) exist before the next step is issued
         return float(loss_host)
 
@@ -377,6 +382,9 @@ def main():
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(5 + i)
+    for kk in (0, 1):
+        if red_work[kk] is not None:
+            red_work[kk].wait()
     barrier()
     e2e_s = time.perf_counter() - t0
 
