@@ -936,16 +936,22 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
 
 // ---------------------------------------------------------------------------------------------------------
 // Generic channel count, k <= 32: threshold selection around an undisturbed FP32 contraction (DGCNN layers 2-4:
-// C = 64, 64, 128). The register-tiled inner product of knn_gemm_kernel (8 queries x 128 candidates per warp step)
-// runs with NO selection in the loop: a lane streams the four scores of each query to a scratch row in the
-// workspace (one coalesced 512-byte store per query and step) and keeps the running maximum of everything it
-// has scored for that query. When the cloud is done, the 32 lane maxima of a query are the maxima of 32 disjoint
-// candidate groups, so their k-th largest value T (warp bitonic sort) is a lower bound of the k-th largest
-// score. Every lane then re-reads the scores it wrote itself (still in L2), the ones >= T (about 31 for k = 20,
-// N = 1024) are compacted into (pd, index) keys, sorted, and the first k indices written. More than 64
-// candidates >= T (massive ties) -> streaming sort-and-merge over the scratch row. Nothing is computed twice;
-// the scratch traffic (4 N^2 bytes per cloud, written once and read once) replaces the reference's three (B,N,N)
-// temporaries and its radix top-k, and stays far below the FP32 time of the contraction.
+// C = 64, 64, 128), two kernels per batch chunk.
+//   knn_rows_kernel    the register-tiled inner product of knn_gemm_kernel (8 queries x 128 candidates per warp
+//                      step, software-pipelined over channels, 16-byte cp.async tiles, two 256-thread CTAs per SM)
+//                      with NO selection at all: a lane streams the four scores of each query to a scratch row in
+//                      the workspace (one coalesced 512-byte store per query and step). The loop runs at the FP32
+//                      pipe's pace (92 % of peak while it runs, ncu).
+//   knn_rows_select_kernel  a warp per query, eight warps per CTA, as many CTAs per SM as fit -- the selection is a
+//                      chain of shuffles and ballots, so it wants thread-level parallelism, not the 16 warps per
+//                      SM the contraction leaves. The warp reads the query's row (coalesced float4, from L2), the
+//                      32 lane maxima are the maxima of 32 disjoint candidate groups, so their k-th largest value T
+//                      (warp bitonic sort) is a lower bound of the k-th largest score; the scores >= T (about 31
+//                      for k = 20, N = 1024) are marked in a 64-bit mask per lane, a warp prefix sum of the counts
+//                      gives every lane its output position, the keys are sorted and the first k indices written.
+//                      More than 64 candidates >= T (massive ties) -> streaming sort-and-merge over the row.
+// Nothing is computed twice; the scratch traffic (4 N^2 bytes per cloud, written once and read once) replaces the
+// reference's three (B,N,N) temporaries and its radix top-k, and stays far below the FP32 time of the contraction.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sort_desc_f32(float v, int lane) {
 #pragma unroll
@@ -960,17 +966,15 @@ __device__ __forceinline__ float warp_sort_desc_f32(float v, int lane) {
     return v;
 }
 
-constexpr int kRowsMaxN = 2048;  // one bit per score of a lane in a 64-bit mask
+constexpr int kRowsMaxN = 2048;  // one bit per score of a lane in a 64-bit mask; 16 float4 of scores per lane
 constexpr int kRowsThreads = 256, kRowsWarps = kRowsThreads / 32;  // two CTAs per SM: one computes while the other loads a tile
 
 __global__ void __launch_bounds__(kRowsThreads, 2)
-knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int k, int J, int npad, float* __restrict__ rows,
-                int64_t* __restrict__ idx) {
+knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int J, int npad, float* __restrict__ rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sTile = reinterpret_cast<float*>(smem_raw);  // [C][J], J a multiple of 128
     float* sXX = sTile + (size_t)C * J;                 // [J]
-    float* sQ = sXX + J;                                // [kRowsWarps][C][kKnnQB]
-    u64* sKey = reinterpret_cast<u64*>(sQ + (size_t)kRowsWarps * C * kKnnQB);  // [kRowsWarps][64]
+    float* sQ = sXX + J;                                // [kRowsWarps][C][kKnnQB] (+ 8 floats: the pipelined loop reads one channel ahead)
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int b = blockIdx.y;
@@ -978,15 +982,11 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
     const float* __restrict__ xb = x + (size_t)b * C * N;
     const float* __restrict__ xxb = xx + (size_t)b * N;
     float* myQ = sQ + (size_t)w * C * kKnnQB;
-    u64* myKey = sKey + w * kSelCap;
     float* myRows = rows + ((size_t)b * N + min(i0, N - 1)) * npad + 4 * lane;  // + q * npad + step * 128
 
-    float xxi[kKnnQB], cm[kKnnQB];
+    float xxi[kKnnQB];
 #pragma unroll
-    for (int q = 0; q < kKnnQB; ++q) {
-        xxi[q] = __ldg(xxb + min(i0 + q, N - 1));
-        cm[q] = -CUDART_INF_F;
-    }
+    for (int q = 0; q < kKnnQB; ++q) xxi[q] = __ldg(xxb + min(i0 + q, N - 1));
     for (int e = lane; e < C * kKnnQB; e += 32) {
         const int c = e / kKnnQB, q = e - c * kKnnQB;
         myQ[e] = __ldg(xb + (size_t)c * N + min(i0 + q, N - 1));
@@ -1038,80 +1038,94 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
 #pragma unroll
                 for (int t = 0; t < kKnnTC; ++t)
                     pd[t] = jl + t < jn ? __fsub_rn(__fmaf_rn(2.0f, dot[q][t], nxx[t]), xxi[q]) : -CUDART_INF_F;  // padding never wins
-                cm[q] = max3(max3(cm[q], pd[0], pd[1]), pd[2], pd[3]);
-                if (i0 + q < N) *reinterpret_cast<float4*>(out + (size_t)q * npad) = make_float4(pd[0], pd[1], pd[2], pd[3]);
+                if (i0 + q < N) __stcg(reinterpret_cast<float4*>(out + (size_t)q * npad), make_float4(pd[0], pd[1], pd[2], pd[3]));
             }
         }
     }
-    if (i0 >= N) return;
+}
 
-    // ---- selection: per query, threshold from the 32 lane maxima, then this lane's own scores again ----
-#pragma unroll 1
-    for (int q = 0; q < kKnnQB; ++q) {
-        if (i0 + q >= N) break;  // warp-uniform
-        float mine = cm[0];      // cm[q] without dynamic register indexing
+constexpr int kRowsSelWarps = 8;
+
+// kRowsSelV = float4 of scores per lane (npad / 128 <= kRowsSelV)
+template <int kRowsSelV>
+__global__ void __launch_bounds__(kRowsSelWarps * 32)
+knn_rows_select_kernel(const float* __restrict__ rows, int N, int k, int npad, int64_t* __restrict__ idx) {
+    __shared__ u64 sKey[kRowsSelWarps][kSelCap];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * kRowsSelWarps + w;
+    if (i >= N) return;  // warp-uniform; no CTA-wide barrier below
+    const float* __restrict__ row = rows + ((size_t)b * N + i) * npad;
+    u64* myKey = sKey[w];
+
+    // the row: lane l holds scores 128 s + 4 l .. + 3 of every step s (the layout the scoring kernel wrote)
+    float4 p[kRowsSelV];
+    float cm = -CUDART_INF_F;
 #pragma unroll
-        for (int z = 1; z < kKnnQB; ++z) mine = z == q ? cm[z] : mine;
-        const float thr = __shfl_sync(0xffffffffu, warp_sort_desc_f32(mine, lane), k - 1);
-        const float* row = myRows + (size_t)q * npad;
-        // this lane's scores >= thr as a bit mask (bit 4*step + t), then positions by a warp prefix sum of the counts
-        u64 mask = 0ull;
-        for (int s0 = 0, bit = 0; s0 < npad; s0 += 128, bit += 4) {  // npad <= 2048 (kRowsMaxN): at most 64 scores per lane
-            const float4 p4 = *reinterpret_cast<const float4*>(row + s0);
-            const int j = s0 + 4 * lane;
-            const unsigned m4 = (j < N && p4.x >= thr ? 1u : 0u) | (j + 1 < N && p4.y >= thr ? 2u : 0u) |
-                                (j + 2 < N && p4.z >= thr ? 4u : 0u) | (j + 3 < N && p4.w >= thr ? 8u : 0u);
-            mask |= (u64)m4 << bit;
+    for (int s_ = 0; s_ < kRowsSelV; ++s_) {
+        if (128 * s_ < npad) {  // warp-uniform
+            p[s_] = __ldcg(reinterpret_cast<const float4*>(row + 128 * s_ + 4 * lane));
+            cm = max3(max3(cm, p[s_].x, p[s_].y), p[s_].z, p[s_].w);
         }
-        const int mine_n = __popcll(mask);
-        int incl = mine_n;
+    }
+    const float thr = __shfl_sync(0xffffffffu, warp_sort_desc_f32(cm, lane), k - 1);
+
+    // scores >= thr as a bit mask (bit 4 s + t), positions by a warp prefix sum of the counts
+    u64 mask = 0ull;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += nb;
+    for (int s_ = 0; s_ < kRowsSelV; ++s_) {
+        if (128 * s_ < npad) {
+            const int j = 128 * s_ + 4 * lane;
+            const unsigned m4 = (j < N && p[s_].x >= thr ? 1u : 0u) | (j + 1 < N && p[s_].y >= thr ? 2u : 0u) |
+                                (j + 2 < N && p[s_].z >= thr ? 4u : 0u) | (j + 3 < N && p[s_].w >= thr ? 8u : 0u);
+            mask |= (u64)m4 << (4 * s_);
         }
-        const int cnt = __shfl_sync(0xffffffffu, incl, 31);
-        __syncwarp();  // the previous query's keys are no longer read
-        if (cnt <= kSelCap) {
-            int pos = incl - mine_n;
-            while (mask) {
-                const int bit = __ffsll((long long)mask) - 1;
-                mask &= mask - 1;
-                const int off = (bit >> 2) * 128 + 4 * lane + (bit & 3);
-                myKey[pos++] = knn_key_of(row[off - 4 * lane], off);
-            }
+    }
+    const int mine_n = __popcll(mask);
+    int incl = mine_n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    const int cnt = __shfl_sync(0xffffffffu, incl, 31);
+
+    u64 key = 0ull;
+    if (cnt <= kSelCap) {
+        int pos = incl - mine_n;
+        while (mask) {
+            const int bit = __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            const int off = (bit >> 2) * 128 + 4 * lane + (bit & 3);
+            myKey[pos++] = knn_key_of(__ldcg(row + off), off);
         }
         __syncwarp();
-        u64 key = 0ull;
-        if (cnt <= kSelCap) {
-            for (int h = 0; h * 32 < cnt; ++h) {
-                const int e = h * 32 + lane;
-                const u64 kb = warp_sort_desc(e < cnt ? myKey[e] : 0ull, lane);
-                if (h == 0) {
-                    key = kb;
-                } else {
-                    const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
-                    key = warp_merge_desc(key > rev ? key : rev, lane);
-                }
-            }
-        } else {
-            // more than 64 candidates tie with the threshold: streaming sort-and-merge over the scratch row
-            const float* rowq = rows + ((size_t)b * N + i0 + q) * npad;  // other lanes' stores: visible after the __syncwarp above
-            u64 tau = 0ull;
-            for (int j0 = 0; j0 < N; j0 += 32) {
-                const int j = j0 + lane;
-                u64 kb = j < N ? knn_key_of(__ldcg(rowq + j), j) : 0ull;
-                if (!(kb > tau)) kb = 0ull;
-                if (__any_sync(0xffffffffu, kb != 0ull)) {
-                    kb = warp_sort_desc(kb, lane);
-                    const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
-                    key = warp_merge_desc(key > rev ? key : rev, lane);
-                    tau = __shfl_sync(0xffffffffu, key, k - 1);
-                }
+        for (int h = 0; h * 32 < cnt; ++h) {
+            const int e = h * 32 + lane;
+            const u64 kb = warp_sort_desc(e < cnt ? myKey[e] : 0ull, lane);
+            if (h == 0) {
+                key = kb;
+            } else {
+                const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
+                key = warp_merge_desc(key > rev ? key : rev, lane);
             }
         }
-        if (lane < k) idx[((size_t)b * N + i0 + q) * k + lane] = (int64_t)(0xffffffffu - (unsigned)key);
+    } else {
+        // more than 64 candidates tie with the threshold: streaming sort-and-merge over the scratch row
+        u64 tau = 0ull;
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const int j = j0 + lane;
+            u64 kb = j < N ? knn_key_of(__ldcg(row + j), j) : 0ull;
+            if (!(kb > tau)) kb = 0ull;
+            if (__any_sync(0xffffffffu, kb != 0ull)) {
+                kb = warp_sort_desc(kb, lane);
+                const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
+                key = warp_merge_desc(key > rev ? key : rev, lane);
+                tau = __shfl_sync(0xffffffffu, key, k - 1);
+            }
+        }
     }
+    if (lane < k) idx[((size_t)b * N + i) * k + lane] = (int64_t)(0xffffffffu - (unsigned)key);
 }
 
 struct KnnPlan {
@@ -1161,7 +1175,7 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
                 p.rows = true;
                 p.npad = (int)npad;
                 p.chunk = (int)chunk;
-                p.smem = ((size_t)C * jg + jg + (size_t)kRowsWarps * C * kKnnQB) * sizeof(float) + (size_t)kRowsWarps * kSelCap * sizeof(u64);
+                p.smem = ((size_t)C * jg + jg + (size_t)kRowsWarps * C * kKnnQB + kKnnQB) * sizeof(float);
                 p.ws_bytes += align_up(row_bytes, 256);
             }
             return p;
@@ -1187,7 +1201,16 @@ static int knn_launch_rows(const float* x, const float* xx, float* rows, int B, 
     for (int b0 = 0; b0 < B; b0 += p.chunk) {
         const int nb = min(p.chunk, B - b0);
         knn_rows_kernel<<<dim3((unsigned)cdiv(N, kRowsWarps * kKnnQB), (unsigned)nb), kRowsThreads, p.smem, stream>>>(
-            x + (size_t)b0 * C * N, xx + (size_t)b0 * N, C, N, k, p.J, p.npad, rows, idx + (size_t)b0 * N * k);
+            x + (size_t)b0 * C * N, xx + (size_t)b0 * N, C, N, p.J, p.npad, rows);
+        FPSG_CUDA_OK(cudaGetLastError());
+        const dim3 sgrid((unsigned)cdiv(N, kRowsSelWarps), (unsigned)nb);
+        int64_t* out = idx + (size_t)b0 * N * k;
+        if (p.npad <= 512)
+            knn_rows_select_kernel<4><<<sgrid, kRowsSelWarps * 32, 0, stream>>>(rows, N, k, p.npad, out);
+        else if (p.npad <= 1024)
+            knn_rows_select_kernel<8><<<sgrid, kRowsSelWarps * 32, 0, stream>>>(rows, N, k, p.npad, out);
+        else
+            knn_rows_select_kernel<16><<<sgrid, kRowsSelWarps * 32, 0, stream>>>(rows, N, k, p.npad, out);
         FPSG_CUDA_OK(cudaGetLastError());
     }
     return FPSG_OK;
