@@ -172,3 +172,50 @@ def test_c3_knn_shape_and_feature_counts():
         x = make_cloud_cn(32 if C == 3 else 4, C, 1024, seed=100 + C)
         got = fpsg_b200.knn(x.cuda(), 20).cpu().numpy()
         assert (got == O.knn_f32(x.numpy(), 20)).all()
+
+
+def test_concurrent_streams_and_threads_do_not_interfere():
+    """SURVEY.md 8b (threading): the entry points take the stream explicitly, hold no global state and own no memory, so
+    calls issued from several host threads onto several CUDA streams at once must give the single-stream results."""
+    import threading
+    import fpsg_b200
+    from tests.helpers import make_cloud_cn, make_pair
+    dev = torch.device("cuda", 0)
+    jobs = []
+    for s in range(4):
+        p1, p2 = make_pair(6, 700 + 13 * s, 650 - 7 * s, seed=100 + s)
+        x = make_cloud_cn(3, 3 if s % 2 == 0 else 16, 500 + s, seed=s)
+        jobs.append((p1.to(dev), p2.to(dev), x.to(dev)))
+    want = []
+    for p1, p2, x in jobs:  # reference results, one after the other on the default stream
+        a = p1.clone().requires_grad_(True)
+        loss = fpsg_b200.chamfer_loss(a, p2)
+        loss.sum().backward()
+        want.append((loss.detach().clone(), a.grad.clone(), fpsg_b200.knn(x, 20)))
+    torch.cuda.synchronize()
+    got = [None] * len(jobs)
+    errors = []
+
+    def work(k):
+        try:
+            st = torch.cuda.Stream(device=dev)
+            st.wait_stream(torch.cuda.default_stream(dev))
+            with torch.cuda.stream(st):
+                for _ in range(5):  # keep several calls in flight per stream
+                    p1, p2, x = jobs[k]
+                    a = p1.clone().requires_grad_(True)
+                    loss = fpsg_b200.chamfer_loss(a, p2)
+                    loss.sum().backward()
+                    got[k] = (loss.detach().clone(), a.grad.clone(), fpsg_b200.knn(x, 20))
+            st.synchronize()
+        except Exception as e:  # pragma: no cover - reported below
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (l0, g0, i0), (l1, g1, i1) in zip(want, got):
+        assert torch.equal(l0, l1) and torch.equal(g0, g1) and torch.equal(i0, i1)
