@@ -53,8 +53,8 @@ __device__ __forceinline__ void cp_async_f32x4(float* smem_dst, const float* gme
 }
 
 // loads the [C][jn] block x[:, j0:j0+jn] and the matching squared norms into shared memory (row stride J)
-__device__ __forceinline__ void knn_load_tile(float* sTile, float* sXX, const float* __restrict__ xb, const float* __restrict__ xxb,
-                                              int C, int N, int J, int j0, int jn, int tid, int nthreads = kKnnThreads) {
+__device__ __forceinline__ void knn_issue_tile(float* sTile, float* sXX, const float* __restrict__ xb, const float* __restrict__ xxb,
+                                               int C, int N, int J, int j0, int jn, int tid, int nthreads = kKnnThreads) {
     const int lane = tid & 31, w = tid >> 5, nwarps = nthreads >> 5;
     // 16-byte copies when every row segment is 16-byte aligned on both sides (J is always a multiple of 32)
     const bool vec = ((N | j0 | jn) & 3) == 0 && (reinterpret_cast<uintptr_t>(xb) & 15) == 0 && (reinterpret_cast<uintptr_t>(xxb) & 15) == 0;
@@ -74,6 +74,10 @@ __device__ __forceinline__ void knn_load_tile(float* sTile, float* sXX, const fl
         }
         for (int jj = tid; jj < jn; jj += nthreads) cp_async_f32(sXX + jj, xxb + j0 + jj);
     }
+}
+__device__ __forceinline__ void knn_load_tile(float* sTile, float* sXX, const float* __restrict__ xb, const float* __restrict__ xxb,
+                                              int C, int N, int J, int j0, int jn, int tid, int nthreads = kKnnThreads) {
+    knn_issue_tile(sTile, sXX, xb, xxb, C, N, J, j0, jn, tid, nthreads);
     cp_async_wait_all();
 }
 
@@ -970,11 +974,13 @@ constexpr int kRowsMaxN = 2048;  // one bit per score of a lane in a 64-bit mask
 constexpr int kRowsThreads = 256, kRowsWarps = kRowsThreads / 32;  // two CTAs per SM: one computes while the other loads a tile
 
 __global__ void __launch_bounds__(kRowsThreads, 2)
-knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int J, int npad, float* __restrict__ rows) {
+knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int J, int npad, int nbuf, float* __restrict__ rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sTile = reinterpret_cast<float*>(smem_raw);  // [C][J], J a multiple of 128
-    float* sXX = sTile + (size_t)C * J;                 // [J]
-    float* sQ = sXX + J;                                // [kRowsWarps][C][kKnnQB] (+ 8 floats: the pipelined loop reads one channel ahead)
+    // nbuf (1 or 2) candidate tiles of [C][J] coordinates + [J] norms each (J a multiple of 128): with two, the next
+    // tile is in flight (cp.async) while the current one is multiplied
+    const size_t tile_floats = (size_t)C * J + J;
+    float* sTiles = reinterpret_cast<float*>(smem_raw);
+    float* sQ = sTiles + nbuf * tile_floats;            // [kRowsWarps][C][kKnnQB] (+ 8 floats: the pipelined loop reads one channel ahead)
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int b = blockIdx.y;
@@ -993,11 +999,23 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
     }
     __syncwarp();
 
-    for (int j0 = 0; j0 < N; j0 += J) {
+    if (nbuf == 2) knn_issue_tile(sTiles, sTiles + (size_t)C * J, xb, xxb, C, N, J, 0, min(J, N), tid, kRowsThreads);
+    for (int j0 = 0, it = 0; j0 < N; j0 += J, ++it) {
         const int jn = min(J, N - j0);
-        __syncthreads();  // previous tile fully consumed
-        knn_load_tile(sTile, sXX, xb, xxb, C, N, J, j0, jn, tid, kRowsThreads);
-        __syncthreads();
+        float* sTile = sTiles + (nbuf == 2 ? (it & 1) * tile_floats : 0);
+        float* sXX = sTile + (size_t)C * J;
+        if (nbuf == 2) {
+            cp_async_wait_all();  // this thread's share of tile `it` has landed ...
+            __syncthreads();      // ... everybody's has, and the other buffer is no longer read
+            if (j0 + J < N) {
+                float* nt = sTiles + ((it + 1) & 1) * tile_floats;
+                knn_issue_tile(nt, nt + (size_t)C * J, xb, xxb, C, N, J, j0 + J, min(J, N - j0 - J), tid, kRowsThreads);
+            }
+        } else {
+            __syncthreads();  // previous tile fully consumed
+            knn_load_tile(sTile, sXX, xb, xxb, C, N, J, j0, jn, tid, kRowsThreads);
+            __syncthreads();
+        }
         if (i0 >= N) continue;  // warp-uniform; the warp still takes part in the barriers
 
         for (int jb = 0; jb < jn; jb += 32 * kKnnTC) {
@@ -1133,6 +1151,7 @@ struct KnnPlan {
     bool rows;   // generic C, k <= 32: knn_rows_kernel (scores streamed to scratch rows in the workspace)
     int npad;    // floats per scratch row
     int chunk;   // clouds per launch of knn_rows_kernel: the scratch (chunk * N rows) is reused by the next launch
+    int nbuf;    // candidate tiles in shared memory (2 = double-buffered, when two CTAs per SM still fit)
     bool gemm;  // generic C, k <= 32: the register-tiled scoring kernel
     int J;
     size_t smem;
@@ -1152,6 +1171,7 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
     p.rows = false;
     p.npad = 0;
     p.chunk = 0;
+    p.nbuf = 1;
     if (p.KR == 1 && C != 3 && !getenv("FPSG_KNN_INSERT") && !getenv("FPSG_KNN_NOGEMM")) {
         long long jg = (long long)(kKnnTileBytes / sizeof(float)) / (C + 1) / 128 * 128;
         if (jg < 128) jg = 128;
@@ -1175,7 +1195,9 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
                 p.rows = true;
                 p.npad = (int)npad;
                 p.chunk = (int)chunk;
-                p.smem = ((size_t)C * jg + jg + (size_t)kRowsWarps * C * kKnnQB + kKnnQB) * sizeof(float);
+                const size_t tile_b = ((size_t)C * jg + jg) * sizeof(float), q_b = ((size_t)kRowsWarps * C * kKnnQB + kKnnQB) * sizeof(float);
+                p.nbuf = 2 * tile_b + q_b <= 110 * 1024 ? 2 : 1;
+                p.smem = p.nbuf * tile_b + q_b;
                 p.ws_bytes += align_up(row_bytes, 256);
             }
             return p;
@@ -1201,7 +1223,7 @@ static int knn_launch_rows(const float* x, const float* xx, float* rows, int B, 
     for (int b0 = 0; b0 < B; b0 += p.chunk) {
         const int nb = min(p.chunk, B - b0);
         knn_rows_kernel<<<dim3((unsigned)cdiv(N, kRowsWarps * kKnnQB), (unsigned)nb), kRowsThreads, p.smem, stream>>>(
-            x + (size_t)b0 * C * N, xx + (size_t)b0 * N, C, N, p.J, p.npad, rows);
+            x + (size_t)b0 * C * N, xx + (size_t)b0 * N, C, N, p.J, p.npad, p.nbuf, rows);
         FPSG_CUDA_OK(cudaGetLastError());
         const dim3 sgrid((unsigned)cdiv(N, kRowsSelWarps), (unsigned)nb);
         int64_t* out = idx + (size_t)b0 * N * k;
