@@ -343,6 +343,55 @@ def main():
     bwd_us = b0.elapsed_time(b1) / n_sweeps * 1e3
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- secondary configurations of BASELINE.json (not the metric; reported for context, rank 0 only) ----
+    secondary = None
+    if rank == 0:
+        def timed(fn, iters=50, warm=5):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize(dev)
+            t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0_.record(stream)
+            for _ in range(iters):
+                fn()
+            t1_.record(stream)
+            torch.cuda.synchronize(dev)
+            return t0_.elapsed_time(t1_) / iters * 1e3
+        secondary = {}
+        gk = torch.Generator(device="cpu").manual_seed(1234 + 3)
+        for C_ in (3, 64):  # c3: DGCNN kNN graph, k=20, B=32, N=1024 (xyz layer; a 64-channel layer for scale)
+            xk = torch.randn(32, C_, 1024, generator=gk).to(dev)
+            ik = torch.empty(32, 1024, 20, dtype=torch.int64, device=dev)
+            nbk = L.fpsg_knn_workspace_bytes(32, C_, 1024, 20)
+            wsk = torch.empty(max(nbk, 1), dtype=torch.uint8, device=dev)
+            us = timed(lambda: _lib.check(L.fpsg_knn_fwd(xk.data_ptr(), 32, C_, 1024, 20, ik.data_ptr(), wsk.data_ptr(), nbk, sp)), 20, 3)
+            secondary[f"knn_k20_B32_N1024_C{C_}"] = {"us_per_call": us, "tflops": (2 * C_ + 2) * 32 * 1024 * 1024 / us / 1e6,
+                                                    "frac_of_fp32_peak": (2 * C_ + 2) * 32 * 1024 * 1024 / us / 1e6 / fp32_peak_tflops}
+            del xk, ik, wsk
+        # c2: one training episode (5 query + 32 support pairs) as the reference issues it (two calls) and as one call
+        qa, qb = ptrs[0]
+        sg2 = (_lib.ChamferSegment * 2)()
+        gp37 = torch.empty(37, N, 3, device=dev)
+        sg2[0].p1, sg2[0].p2, sg2[0].gp1, sg2[0].gp2, sg2[0].batch, sg2[0].weight = qa, qb, gp37.data_ptr(), None, 5, 1.0
+        sg2[1].p1, sg2[1].p2, sg2[1].gp1, sg2[1].gp2, sg2[1].batch, sg2[1].weight = (ptrs[1][0], ptrs[1][1], gp37.data_ptr() + 5 * N * 12, None,
+                                                                                   32, 1.0)
+        nb37 = L.fpsg_chamfer_fwd_workspace_bytes(37, N, M)
+        ws37 = torch.empty(nb37, dtype=torch.uint8, device=dev)
+        i37 = torch.empty(37 * (N + M), dtype=torch.int64, device=dev)
+        l37 = torch.empty(37 + 3, device=dev)
+        g1_ = torch.ones((), device=dev)
+
+        def two_calls():
+            for (a_, b_), nb_ in ((ptrs[0], 5), (ptrs[1], 32)):
+                _lib.check(L.fpsg_chamfer_loss_fwd(a_, b_, nb_, N, M, 1.0, 1.0, o[0], None, None, o[3], o[4], o[5], nbytes, sp))
+                _lib.check(L.fpsg_chamfer_loss_bwd(a_, b_, o[3], o[4], o[6], 1.0, 1.0, nb_, N, M, o[7], None, None, 0, sp))
+
+        def one_call():
+            _lib.check(L.fpsg_chamfer_multi_loss_fwd(sg2, 2, N, M, 1.0, 1.0, l37.data_ptr() + 12, l37.data_ptr(), i37.data_ptr(),
+                                                     i37.data_ptr() + 8 * 37 * N, ws37.data_ptr(), nb37, sp))
+            _lib.check(L.fpsg_chamfer_multi_loss_bwd(sg2, 2, i37.data_ptr(), i37.data_ptr() + 8 * 37 * N, g1_.data_ptr(), 1.0, 1.0, N, M, sp))
+        secondary["c2_episode_5q_32s"] = {"two_calls_us": timed(two_calls), "multi_segment_us": timed(one_call)}
+
     # ---- end to end: the reference-facing call, host (pinned) inputs, loss read back every step ----
     fpsg_b200.shims.install(force=True)
     from kaolin.metrics.pointcloud import chamfer_distance as shim_chamfer
@@ -430,6 +479,7 @@ def main():
                              "unit": "GB/s", "us_per_launch": bwd_us, "algorithmic_bytes_per_launch": bwd_bytes,
                              "note": "3.9 MB working set is L2-resident: latency-, not bandwidth-bound (SURVEY.md 8d)"},
             "clocks": clocks,
+            "secondary": secondary,
         }
         line["roofline_bwd"]["frac"] = line["roofline_bwd"]["achieved"] / line["roofline_bwd"]["peak"]
         if world == 1 and not args.no_cpu_baseline:
