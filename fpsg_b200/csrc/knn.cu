@@ -627,8 +627,9 @@ constexpr int kSelThreads = 256;
 constexpr int kSelQ = kSelThreads / kSelS;      // queries per CTA
 constexpr int kSelGroups = 32;                  // coarse groups (>= k)
 constexpr int kSelFine = 128;                   // most fine groups per cloud
-constexpr int kSelFmStride = kSelFine + 1;      // floats per query row of the fine maxima (conflict-free both ways)
-constexpr int kSelCap = 64;                     // candidates per query (and per thread column)
+constexpr int kSelFmStride = kSelFine + 2;      // 16-bit elements per query row of the fine maxima (65 words: conflict-free)
+constexpr int kSelCap = 64;                     // candidates per query
+constexpr int kSelColCap = 48;                  // candidate slots per thread column (one of the four shares of a query)
 constexpr int kSelListStride = kSelCap + 2;     // u16 elements per query row of the candidate lists
 constexpr int kSelMaxN = 8192;                  // the cloud must fit shared memory as float4
 
@@ -674,9 +675,9 @@ struct KnnSelPlan {
     int npad;    // nfine << fsh
     size_t smem;
 };
-constexpr size_t kSelRegionA = (size_t)kSelQ * kSelFmStride * sizeof(float);  // fine maxima, later the candidate columns
-constexpr size_t kSelRegionB = (size_t)kSelQ * kSelListStride * sizeof(unsigned short);  // threshold scratch, group lists, query lists
-static_assert(kSelRegionA >= (size_t)kSelCap * kSelThreads * sizeof(unsigned short), "candidate columns fit the fine-maxima region");
+constexpr size_t kSelRegionA = (size_t)kSelColCap * kSelThreads * sizeof(unsigned short);  // fine maxima, later the candidate columns
+constexpr size_t kSelRegionB = (size_t)kSelQ * kSelListStride * sizeof(unsigned short);    // coarse maxima, group lists, query lists
+static_assert(kSelRegionA >= (size_t)kSelQ * kSelFmStride * sizeof(unsigned short), "fine maxima fit the candidate-column region");
 static_assert(kSelRegionB >= (size_t)kSelGroups * kSelQ * sizeof(float) && kSelRegionB >= (size_t)(kSelFine / kSelS) * kSelThreads,
               "region B holds the sorted group maxima and the per-thread group lists");
 static KnnSelPlan knn_select_plan(int N) {
@@ -686,7 +687,7 @@ static KnnSelPlan knn_select_plan(int N) {
     p.nfine = (N + (1 << p.fsh) - 1) >> p.fsh;
     p.npad = p.nfine << p.fsh;
     p.smem = (size_t)(p.npad + (1 << p.fsh)) * sizeof(float4) + kSelRegionA + kSelRegionB + (size_t)kSelQ * sizeof(float) +
-             (size_t)kSelThreads * sizeof(int) + (size_t)kSelQ * sizeof(int);
+             (size_t)kSelThreads * sizeof(signed char) + (size_t)kSelQ * sizeof(signed char);  // ~50 KB at N = 1024: four CTAs per SM
     return p;
 }
 
@@ -698,14 +699,14 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     float4* sTile = reinterpret_cast<float4*>(smem_raw);                              // [ntile] (x, y, z, -xx)
     unsigned char* regA = reinterpret_cast<unsigned char*>(sTile + ntile);
     unsigned char* regB = regA + kSelRegionA;
-    float* sFm = reinterpret_cast<float*>(regA);                                      // [Q][129] fine group maxima ...
-    unsigned short* sBuf = reinterpret_cast<unsigned short*>(regA);                   // ... then [cap][T] candidate columns
-    float* sScr = reinterpret_cast<float*>(regB);                                     // [32][Q] sorted coarse maxima ...
+    unsigned short* sFm = reinterpret_cast<unsigned short*>(regA);                    // [Q][130] fine group maxima, rounded UP to 16 bits ...
+    unsigned short* sBuf = reinterpret_cast<unsigned short*>(regA);                   // ... then [48][T] candidate columns
+    float* sScr = reinterpret_cast<float*>(regB);                                     // [32][Q] exact coarse maxima (then sorted) ...
     unsigned char* sGl = regB;                                                        // ... then [32][T] fine groups to re-score ...
     unsigned short* sList = reinterpret_cast<unsigned short*>(regB);                  // ... then [Q][66] candidates of a query
     float* sThr = reinterpret_cast<float*>(regB + kSelRegionB);                       // [Q]
-    int* sCntP = reinterpret_cast<int*>(sThr + kSelQ);                                // [T] candidates found by a thread, -1 = overflow
-    int* sCnt = sCntP + kSelThreads;                                                  // [Q] candidates of a query, -1 = overflow
+    signed char* sCntP = reinterpret_cast<signed char*>(sThr + kSelQ);                // [T] candidates found by a thread, -1 = overflow
+    signed char* sCnt = sCntP + kSelThreads;                                          // [Q] candidates of a query, -1 = overflow
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int wq = w / kSelS, part = w - wq * kSelS;  // warps wq*4 .. wq*4+3 share 32 queries
@@ -733,49 +734,56 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     const int octs = 1 << (fsh - 3);
 
     // ---- pass 1: maxima of this warp's quarter of the fine groups, one query per thread ----
+    // The fine maxima are kept rounded UP to 16 bits (they only decide which groups are re-scored: a superset is fine);
+    // the threshold needs exact values and gets the exact maxima of the 32 coarse groups (consecutive fine groups).
     {
-        float* fm = sFm + ql * kSelFmStride;
-        if (fsh == 3) {  // one octet per fine group (N <= 1024): no inner loop
-#pragma unroll 2
-            for (int f = f0; f < f1; ++f) {
-                const float4* tp = sTile + (f << 3);
-                float p[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) p[u] = knn_pd3(q, xxi, tp[u]);
-                fm[f] = max3(max3(max3(p[0], p[1], p[2]), p[3], p[4]), max3(p[5], p[6], p[7]), p[0]);
-            }
-        } else {
+        unsigned short* fm = sFm + ql * kSelFmStride;
+        auto up16 = [](float v) {  // smallest 16-bit-truncated float >= v (truncation moves negative values up already)
+            const unsigned u = __float_as_uint(v);
+            return (unsigned short)(((u >> 31) ? u : u + 0xffffu) >> 16);
+        };
 #pragma unroll 1
-            for (int f = f0; f < f1; ++f) {
-                const float4* tp = sTile + (f << fsh);
-                float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+        for (int c = part * (kSelGroups / kSelS); c < (part + 1) * (kSelGroups / kSelS); ++c) {
+            const int fb = (c * nfine) / kSelGroups, fe = ((c + 1) * nfine) / kSelGroups;  // at most 4 fine groups
+            float cmax = -CUDART_INF_F;
+            if (fsh == 3) {  // one octet per fine group (N <= 1024): no inner loop
 #pragma unroll 2
-                for (int o = 0; o < octs; ++o, tp += 8) {
+                for (int f = fb; f < fe; ++f) {
+                    const float4* tp = sTile + (f << 3);
                     float p[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) p[u] = knn_pd3(q, xxi, tp[u]);
-                    m0 = max3(max3(m0, p[0], p[1]), p[2], p[3]);
-                    m1 = max3(max3(m1, p[4], p[5]), p[6], p[7]);
+                    const float m = max3(max3(max3(p[0], p[1], p[2]), p[3], p[4]), max3(p[5], p[6], p[7]), p[0]);
+                    fm[f] = up16(m);
+                    cmax = fmaxf(cmax, m);
                 }
-                fm[f] = max3(m0, m0, m1);
+            } else {
+                for (int f = fb; f < fe; ++f) {
+                    const float4* tp = sTile + (f << fsh);
+                    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+#pragma unroll 2
+                    for (int o = 0; o < octs; ++o, tp += 8) {
+                        float p[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) p[u] = knn_pd3(q, xxi, tp[u]);
+                        m0 = max3(max3(m0, p[0], p[1]), p[2], p[3]);
+                        m1 = max3(max3(m1, p[4], p[5]), p[6], p[7]);
+                    }
+                    const float m = max3(m0, m0, m1);
+                    fm[f] = up16(m);
+                    cmax = fmaxf(cmax, m);
+                }
             }
+            sScr[c * kSelQ + ql] = cmax;
         }
     }
     __syncthreads();
 
     // ---- threshold: k-th largest of the 32 coarse group maxima (bitonic network in registers) ----
     if (part == 0) {
-        const float* fm = sFm + ql * kSelFmStride;
         float v[kSelGroups];
 #pragma unroll
-        for (int c = 0; c < kSelGroups; ++c) {
-            const int fb = (c * nfine) / kSelGroups, fe = ((c + 1) * nfine) / kSelGroups;  // at most 4 fine groups
-            float m = -CUDART_INF_F;
-#pragma unroll
-            for (int r = 0; r < kSelFine / kSelGroups; ++r)
-                if (fb + r < fe) m = fmaxf(m, fm[fb + r]);
-            v[c] = m;
-        }
+        for (int c = 0; c < kSelGroups; ++c) v[c] = sScr[c * kSelQ + ql];
 #pragma unroll
         for (int s = 2; s <= kSelGroups; s <<= 1) {
 #pragma unroll
@@ -803,11 +811,11 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     // ---- this thread's fine groups whose maximum reaches the threshold: a private list (branch-free append) ----
     int ngl = 0;
     {
-        const float* fm = sFm + ql * kSelFmStride;
+        const unsigned short* fm = sFm + ql * kSelFmStride;
         unsigned char* gl = sGl + tid;
         for (int f = f0; f < f1; ++f) {
             gl[ngl * kSelThreads] = (unsigned char)f;
-            ngl += fm[f] >= thr ? 1 : 0;
+            ngl += __uint_as_float((unsigned)fm[f] << 16) >= thr ? 1 : 0;
         }
     }
     __syncthreads();  // every read of the fine maxima is done: their region becomes the candidate columns
@@ -819,7 +827,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
         for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
         const unsigned col = static_cast<unsigned>(__cvta_generic_to_shared(sBuf + tid));
         const unsigned stepb = 2u * kSelThreads;
-        const unsigned limit = col + (kSelCap - 8) * stepb;
+        const unsigned limit = col + (kSelColCap - 8) * stepb;
         unsigned p = col;
         bool ovf = false;
 #pragma unroll 1
@@ -852,7 +860,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
                 }
             }
         }
-        sCntP[tid] = ovf ? -1 : (int)((p - col) / stepb);
+        sCntP[tid] = ovf ? (signed char)-1 : (signed char)((p - col) / stepb);
     }
     __syncthreads();
 
@@ -872,7 +880,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
             const int mine = sCntP[tid];
             for (int e = 0; e < mine; ++e) sList[ql * kSelListStride + before + e] = sBuf[e * kSelThreads + tid];
         }
-        if (part == 0) sCnt[ql] = ovf ? -1 : total;
+        if (part == 0) sCnt[ql] = ovf ? (signed char)-1 : (signed char)total;
     }
     __syncthreads();
 
