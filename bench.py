@@ -445,11 +445,39 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- the same step through the C ABI itself with host buffers (what a native binding of the reference gets, without
+    # the autograd engine): H2D copy of the step's inputs from pinned memory, fused loss forward with the batch sum,
+    # backward to p1, D2H read of the scalar, stream synchronised -- every step. (Copying the next step's inputs on a
+    # second stream was tried and changes nothing: the step is host issue time + device time, not copy time.) ----
+    cabi_tot = torch.zeros(2, device=dev)
+    cabi_seg = (_lib.ChamferSegment * 1)()
+    cabi_seg[0].p1, cabi_seg[0].p2, cabi_seg[0].gp1, cabi_seg[0].gp2 = dbuf.data_ptr(), dbuf.data_ptr() + 4 * n1, None, None
+    cabi_seg[0].batch, cabi_seg[0].weight = B, 1.0
+    p1d, p2d = dbuf.data_ptr(), dbuf.data_ptr() + 4 * n1
+
+    def cabi_step(i):
+        dbuf.copy_(host[i % len(host)], non_blocking=True)
+        _lib.check(L.fpsg_chamfer_multi_loss_fwd(cabi_seg, 1, N, M, 1.0, 1.0, o[0], cabi_tot.data_ptr(), o[3], o[4], o[5], nbytes, sp))
+        _lib.check(L.fpsg_chamfer_loss_bwd(p1d, p2d, o[3], o[4], o[6], 1.0, 1.0, B, N, M, o[7], None, None, 0, sp))
+        loss_host.copy_(cabi_tot[0], non_blocking=True)
+        cur.synchronize()
+        return float(loss_host)
+
+    with torch.no_grad():
+        for i in range(5):
+            cabi_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            cabi_step(5 + i)
+        barrier()
+        cabi_s = time.perf_counter() - t0
+
     # ---- reduce over ranks (max time) ----
     if world > 1:
-        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, cabi_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms, e2e_s, cabi_s = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         pairs = world * B
@@ -468,6 +496,10 @@ def main():
                        "launch": "C ABI via ctypes, stream-ordered, no CUDA graph"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "api": "kaolin.metrics.pointcloud.chamfer_distance(p1, p2).sum().backward() (fpsg_b200 shim); every step: one H2D copy of its inputs from pinned host memory, forward, backward, loss read back to the host, stream synchronised"},
+            "e2e_c_abi": {"value": pairs * e2e_steps / cabi_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": 4,
+                          "steps": e2e_steps,
+                          "api": "fpsg_chamfer_multi_loss_fwd + fpsg_chamfer_loss_bwd through ctypes (no autograd); every step: one H2D copy of "
+                                 "its inputs from pinned host memory, forward, backward, loss sum read back to the host, stream synchronised"},
             "gpu_launches": kernels_per_step * args.steps,
             "roofline": {"bound": "fp32_fma", "kernel": "chamfer_sweep_kernel<16,false>", "achieved": achieved, "peak": fp32_peak_tflops,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": SWEEP_DRAM_TRAFFIC_BYTES,
