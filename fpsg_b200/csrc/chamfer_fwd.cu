@@ -434,9 +434,13 @@ struct FinalizeArgs {
     int nrb, ncb;
     float* totals;       // [1 + segments]: weighted total and per-segment sums of loss (nullptr: not wanted)
     int B;
+    int stage;           // the cloud whose points are re-evaluated is staged in (dynamic) shared memory
 };
 
-__global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const FinalizeArgs a) {
+constexpr size_t kFinStageMaxBytes = 64 * 1024;    // clouds up to this size are staged
+
+__global__ void __launch_bounds__(kFinThreads, 4) chamfer_finalize_kernel(const FinalizeArgs a) {
+    extern __shared__ __align__(16) float sCloud[];    // staged candidate cloud: p2[b] for row CTAs, p1[b] for column CTAs
     __shared__ __align__(16) float4 sPt[kFinThreads];  // (x, y, z, minimum) of the thread's point
     __shared__ int sBase[kFinThreads];                  // first candidate index to re-evaluate
     __shared__ int sFound[kFinThreads];
@@ -450,7 +454,29 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
     const int TN = kSweepThreads * a.R;
     float mine = 0.f;  // this thread's distance, for the loss partial
     cudaTriggerProgrammaticLaunchCompletion();  // a following backward may start to launch
+    // Staging: the arg-min re-evaluation reads a few candidates per point from anywhere in the other cloud -- dependent,
+    // scattered global loads. The clouds are inputs, complete before the sweep (this grid's only predecessor) started, so
+    // their loads may be issued ahead of the dependency wait; they land in shared memory while the partials are merged.
+    const bool rowcta = blk < a.nrb;
+    const float* __restrict__ csrc = rowcta ? p2b : p1b;
+    const int cfl = 3 * (rowcta ? a.M : a.N);
+    const bool cvec = a.stage && (reinterpret_cast<uintptr_t>(csrc) & 15) == 0;
+    const int c4 = cvec ? cfl >> 2 : 0;
+    if (cvec) {
+        const unsigned sdst = (unsigned)__cvta_generic_to_shared(sCloud);
+        for (int q = tid; q < c4; q += kFinThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16u * q), "l"(reinterpret_cast<const float4*>(csrc) + q) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     cudaGridDependencySynchronize();            // the sweep's partials are complete and visible from here on
+    auto stage_cloud = [&]() {  // what the asynchronous copies do not cover (unaligned cloud, last 1-3 floats), then wait for them
+        if (!a.stage) return;
+        for (int q = 4 * c4 + tid; q < cfl; q += kFinThreads) sCloud[q] = __ldg(csrc + q);
+        // +INF up to the next multiple of 32 points: a candidate window may run past the end of the cloud, and a padded
+        // point never equals a minimum
+        for (int q = cfl + tid; q < 3 * ((cfl / 3 + 31) & ~31); q += kFinThreads) sCloud[q] = CUDART_INF_F;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    };
 
     // Loss partial of this CTA: needs only the merged minima, so it is issued before the arg-min re-evaluation and
     // the latency of the arrival-counter atomic hides behind that phase. Fixed-order block sum in double (lanes by
@@ -493,26 +519,47 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
                 u64 v[kSlotBatch];
 #pragma unroll
                 for (int s = 0; s < kSlotBatch; ++s) v[s] = s0 + s < nsl ? rp[(size_t)(s0 + s) * TN] : ~0ull;
+                if (s0 == 0) {
+                    ax = __ldg(p1b + 3 * i);
+                    ay = __ldg(p1b + 3 * i + 1);
+                    az = __ldg(p1b + 3 * i + 2);
+                }
 #pragma unroll
                 for (int s = 0; s < kSlotBatch; ++s) key = v[s] < key ? v[s] : key;
             }
             m = __uint_as_float((unsigned)(key >> 32));
             sub = (int)(unsigned)key;
-            ax = __ldg(p1b + 3 * i);
-            ay = __ldg(p1b + 3 * i + 1);
-            az = __ldg(p1b + 3 * i + 2);
             mine = m;
         }
+        stage_cloud();
         sPt[tid] = make_float4(ax, ay, az, m);
         sBase[tid] = sub * kSub;
         __syncwarp();
-        if (a.losspart) loss_partial(mine);
+        if (a.losspart) loss_partial(mine);  // (contains the CTA barrier that also publishes the staged cloud)
+        else if (a.stage) __syncthreads();
         // ... then the warp re-evaluates the kSub columns of every row's winning sub-block together (coalesced);
         // the lowest lane whose distance equals the minimum bit-for-bit is the arg-min. Lanes past the end of the
         // cloud re-evaluate the last column: they can only tie with a lower lane that holds the same column.
         const int last = a.M - 1;
-        constexpr int kBatch = 8;  // rows whose candidate loads are put in flight together (the loop is latency-bound)
         constexpr int kH = kSub / 32;
+        if (a.stage) {
+            // staged: every thread scans the kSub candidates of its own row, starting at a lane-dependent rotation (the
+            // windows start on multiples of 32 points = 96 floats, so un-rotated all lanes would hit the same bank);
+            // the lowest matching index is the arg-min whatever the visiting order
+            const float* win = sCloud + 3 * (sub * kSub);
+            int f = 0x7fffffff;
+#pragma unroll 8
+            for (int c = 0; c < kSub; ++c) {
+                const int o = (lane + c) & (kSub - 1);
+                const float d = sqdist(ax, ay, az, win[3 * o], win[3 * o + 1], win[3 * o + 2]);
+                if (d == m) f = min(f, o);
+            }
+            if (valid) {
+                if (a.dist1) a.dist1[(size_t)b * a.N + i] = m;
+                a.idx1[(size_t)b * a.N + i] = f == 0x7fffffff ? sub * kSub : sub * kSub + f;
+            }
+        } else {
+        constexpr int kBatch = 8;  // rows whose candidate loads are put in flight together (the loop is latency-bound)
         for (int rb = 0; rb < 32; rb += kBatch) {
             float cx[kBatch][kH], cy[kBatch][kH], cz[kBatch][kH];
 #pragma unroll
@@ -544,8 +591,9 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
                 if (lane == 0) sFound[w * 32 + rb + r] = f;
             }
         }
+        }
         __syncwarp();
-        if (valid) {
+        if (valid && !a.stage) {
             if (a.dist1) a.dist1[(size_t)b * a.N + i] = m;
             a.idx1[(size_t)b * a.N + i] = sFound[tid];
         }
@@ -572,14 +620,31 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
             qz = __ldg(p2b + 3 * j + 2);
             mine = m;
         }
+        stage_cloud();
         sPt[tid] = make_float4(qx, qy, qz, m);
         sBase[tid] = r0;
         __syncwarp();
         if (a.losspart) loss_partial(mine);
+        else if (a.stage) __syncthreads();
         // ... then groups of R lanes re-evaluate the R consecutive rows of each column's winning thread (coalesced)
         const int R = a.R, per = 32 / R, grp = lane / R, off = lane - grp * R;
         const unsigned gmask = ((1u << R) - 1u) << (grp * R);  // R <= 16
         const int last = a.N - 1;
+        if (a.stage) {
+            // staged: every thread scans the R rows of its own column's winning thread, rotated by the lane number
+            const float* win = sCloud + 3 * r0;
+            int f = 0x7fffffff;
+#pragma unroll 4
+            for (int c = 0; c < R; ++c) {
+                const int o = (lane + c) & (R - 1);
+                const float d = sqdist(qx, qy, qz, win[3 * o], win[3 * o + 1], win[3 * o + 2]);
+                if (d == m) f = min(f, o);
+            }
+            if (valid) {
+                if (a.dist2) a.dist2[(size_t)b * a.M + j] = m;
+                a.idx2[(size_t)b * a.M + j] = f == 0x7fffffff ? min(r0, last) : r0 + f;
+            }
+        } else {
         constexpr int kCB = 4;  // iterations whose candidate loads are in flight together (R is a multiple of 4)
         for (int ib = 0; ib < R; ib += kCB) {
             float rx[kCB], ry[kCB], rz[kCB];
@@ -601,8 +666,9 @@ __global__ void __launch_bounds__(kFinThreads) chamfer_finalize_kernel(const Fin
                 if (off == 0) sFound[c] = hit ? min(rr0 + (__ffs(hit) - 1 - grp * R), last) : min(rr0, last);
             }
         }
+        }
         __syncwarp();
-        if (valid) {
+        if (valid && !a.stage) {
             if (a.dist2) a.dist2[(size_t)b * a.M + j] = m;
             a.idx2[(size_t)b * a.M + j] = sFound[tid];
         }
@@ -691,10 +757,20 @@ int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist
     else
         FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<4, false>, sgrid, sblock, 0, stream, sa));
     if (sweep_only) return FPSG_OK;
-    const FinalizeArgs fa{seg, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart,
-                          dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb, totals, B};
+    FinalizeArgs fa{seg, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart,
+                          dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb, totals, B, 0};
     const dim3 fgrid((unsigned)(pl.nrb + pl.ncb), (unsigned)B);
-    FPSG_CUDA_OK(launch_pdl(chamfer_finalize_kernel, fgrid, dim3(kFinThreads), 0, stream, fa));
+    size_t fin_smem = align_up((size_t)(N > M ? N : M), 32) * 12;  // whole 32-point windows
+    static const bool no_stage = getenv("FPSG_FIN_NOSTAGE") != nullptr;  // tuning override (benchmarks only)
+    if (fin_smem <= kFinStageMaxBytes && !no_stage) {
+        static const cudaError_t attr_rc =
+            cudaFuncSetAttribute(chamfer_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinStageMaxBytes);
+        FPSG_CUDA_OK(attr_rc);
+        fa.stage = 1;
+    } else {
+        fin_smem = 0;
+    }
+    FPSG_CUDA_OK(launch_pdl(chamfer_finalize_kernel, fgrid, dim3(kFinThreads), fin_smem, stream, fa));
     FPSG_CUDA_OK(cudaGetLastError());
     return FPSG_OK;
 }
