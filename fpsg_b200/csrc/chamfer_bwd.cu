@@ -14,12 +14,15 @@
 // gradient privately in double. The sum is therefore independent of any floating-point atomic ordering (the
 // bucket order is arbitrary, but a double sum of FP32 terms is exact to far below FP32 resolution), matches the
 // oracle's double accumulation, and the gradient is written exactly once, coalesced, with no pre-zeroing.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fpsg {
 
 constexpr int kBwdThreads = 256;
 constexpr int kBwdChunk = 2048;  // arg-min indices of the other cloud scanned per CSR build
+constexpr size_t kBwdStageMaxBytes = 32 * 1024;  // other clouds up to this size are staged (beyond, a CTA would copy more than it gathers)
 
 struct BwdSide {
     bool first;            // A = the p1 side of the segment table (gradient to gp1), else the p2 side
@@ -41,7 +44,8 @@ __device__ __forceinline__ float uniform_weight(float gloss, float scale, float 
 // seg: where the clouds and the gradient outputs live. gtotal (multi-segment loss only): device scalar, the
 // upstream gradient of the weighted total; the pairs of segment s then receive gloss = gtotal * weight_s.
 __global__ void __launch_bounds__(kBwdThreads)
-chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, const float* __restrict__ gtotal) {
+chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, const float* __restrict__ gtotal, bool stage) {
+    extern __shared__ __align__(16) float sQ[];  // stage: the other cloud of this pair (every gathered edge ends there)
     __shared__ int sCount[kBwdThreads];
     __shared__ int sCursor[kBwdThreads];
     __shared__ int sWarp[kBwdThreads / 32];
@@ -77,6 +81,19 @@ chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, con
 
     constexpr int kPer = kBwdChunk / kBwdThreads;  // arg-min indices of the other cloud per thread per chunk
 
+    // Staging (clouds up to 64 KB): the other cloud is copied to shared memory asynchronously while the indices are loaded
+    // and the inverted index is built, so the gathers below are shared-memory reads instead of dependent L2 round trips.
+    // (Issued after the dependency wait: unlike in the forward, the previous kernel in the stream may be the clouds' producer.)
+    if (stage) {
+        const int qfl = 3 * S.Nq;
+        const int q4 = (reinterpret_cast<uintptr_t>(Qb) & 15) == 0 ? qfl >> 2 : 0;
+        const unsigned sdst = (unsigned)__cvta_generic_to_shared(sQ);
+        for (int q = tid; q < q4; q += kBwdThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16u * q), "l"(reinterpret_cast<const float4*>(Qb) + q) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int q = 4 * q4 + tid; q < qfl; q += kBwdThreads) sQ[q] = __ldg(Qb + q);
+    }
+
     // issue order matters more than arithmetic here (the kernel is a chain of L2 latencies): own point and its
     // direct edge first, then the first chunk of the other cloud's indices, all in flight together
     float ax = 0.f, ay = 0.f, az = 0.f;
@@ -98,11 +115,15 @@ chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, con
     float dqx = 0.f, dqy = 0.f, dqz = 0.f, gdir = 0.f;
     if (live) {
         gdir = uniform ? uA : __fmul_rn(2.0f, __ldg(S.gA + (size_t)b * S.Na + i));
-        dqx = __ldg(Qb + 3 * x);
-        dqy = __ldg(Qb + 3 * x + 1);
-        dqz = __ldg(Qb + 3 * x + 2);
+        if (!stage) {
+            dqx = __ldg(Qb + 3 * x);
+            dqy = __ldg(Qb + 3 * x + 1);
+            dqz = __ldg(Qb + 3 * x + 2);
+        }
     }
     double gx = 0.0, gy = 0.0, gz = 0.0;
+    if (stage) asm volatile("cp.async.wait_group 0;" ::: "memory");  // published by the first barrier of the build below
+    const float* __restrict__ Qg = stage ? sQ : Qb;                   // where the gathers read
 
     for (int j0 = 0; j0 < S.Nq; j0 += kBwdChunk) {
         const int jn = min(kBwdChunk, S.Nq - j0);
@@ -143,6 +164,11 @@ chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, con
         // gather: this thread's bucket, four edges in flight at a time (each is a dependent L2 round trip)
         if (live) {
             if (j0 == 0) {
+                if (stage) {
+                    dqx = sQ[3 * x];
+                    dqy = sQ[3 * x + 1];
+                    dqz = sQ[3 * x + 2];
+                }
                 gx = (double)__fmul_rn(gdir, __fsub_rn(ax, dqx));
                 gy = (double)__fmul_rn(gdir, __fsub_rn(ay, dqy));
                 gz = (double)__fmul_rn(gdir, __fsub_rn(az, dqz));
@@ -154,9 +180,9 @@ chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, con
                     const bool on = e + v < start + c;
                     const int j = on ? sList[e + v] : 0;
                     gg[v] = !on ? 0.f : (uniform ? uQ : __fmul_rn(2.0f, __ldg(S.gQ + (size_t)b * S.Nq + j)));
-                    qx[v] = on ? __ldg(Qb + 3 * j) : ax;
-                    qy[v] = on ? __ldg(Qb + 3 * j + 1) : ay;
-                    qz[v] = on ? __ldg(Qb + 3 * j + 2) : az;
+                    qx[v] = on ? Qg[3 * j] : ax;
+                    qy[v] = on ? Qg[3 * j + 1] : ay;
+                    qz[v] = on ? Qg[3 * j + 2] : az;
                 }
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -195,7 +221,17 @@ int chamfer_backward_launch(const SegTable& seg, const int64_t* idx1, const int6
     BwdSide s1{true, idx1, idx2, g1, g2, w1, w2, (float)N, (float)M, N, M, want1 ? cdiv(N, kBwdThreads) : 0};
     BwdSide s2{false, idx2, idx1, g2, g1, w2, w1, (float)M, (float)N, M, N, want2 ? cdiv(M, kBwdThreads) : 0};
     const dim3 grid((unsigned)(s1.blocks + s2.blocks), (unsigned)B);
-    FPSG_CUDA_OK(launch_pdl(chamfer_bwd_kernel, grid, dim3(kBwdThreads), 0, stream, seg, s1, s2, uniform, gtotal));
+    size_t smem = align_up((size_t)(N > M ? N : M) * 12, 16);
+    static const bool no_stage = getenv("FPSG_BWD_NOSTAGE") != nullptr;  // tuning override (benchmarks only)
+    bool stage = smem <= kBwdStageMaxBytes && !no_stage;
+    if (stage) {
+        static const cudaError_t attr_rc =
+            cudaFuncSetAttribute(chamfer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdStageMaxBytes);
+        FPSG_CUDA_OK(attr_rc);
+    } else {
+        smem = 0;
+    }
+    FPSG_CUDA_OK(launch_pdl(chamfer_bwd_kernel, grid, dim3(kBwdThreads), smem, stream, seg, s1, s2, uniform, gtotal, stage));
     return FPSG_OK;
 }
 
