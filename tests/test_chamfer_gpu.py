@@ -26,6 +26,7 @@ def _run_fwd(p1, p2):
 SHAPES = [
     (1, 1, 1), (2, 1, 70), (2, 70, 1), (3, 31, 33), (2, 64, 64), (1, 513, 129), (2, 2047, 2049), (1, 2049, 2047),
     (37, 100, 90), (4, 2048, 2048), (1, 4100, 300), (2, 300, 4100), (1, 5000, 5000),
+    (1, 5461, 5462), (2, 6000, 300), (1, 5600, 6100),  # around and past the finalize kernel's shared-memory staging limit
 ]
 
 
@@ -84,7 +85,7 @@ def test_large_magnitude_coordinates():
     assert (i1 == oi1).all() and (i2 == oi2).all() and (d1 == od1).all() and (d2 == od2).all()
 
 
-@pytest.mark.parametrize("B,N,M", [(2, 64, 48), (3, 33, 130), (2, 1000, 777), (32, 2048, 2048)])
+@pytest.mark.parametrize("B,N,M", [(2, 64, 48), (3, 33, 130), (2, 1000, 777), (32, 2048, 2048), (2, 2731, 2049), (1, 4100, 5000)])
 def test_backward_vs_oracle_random_upstream(B, N, M):
     import fpsg_b200
     O = _oracle()
