@@ -42,7 +42,7 @@ constexpr int kSweepThreads = 128;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kUnit = 16;           // columns per scheduling unit
 constexpr int kSub = 32;            // columns per shared-memory sub-block (2 units)
-constexpr int kFinThreads = 256;
+
 
 // resident sweep CTAs per SM (register-limited): the persistent grid is this times the SM count
 constexpr int sweep_ctas_per_sm(int R, bool packed) { return packed ? 3 : (R >= 16 ? 4 : 6); }
@@ -58,6 +58,7 @@ struct ChamferPlan {
     int q, r;         // CTA g owns q + (g < r) units starting at g*q + min(g, r)
     int maxslots;     // most CTAs that can intersect one (pair, strip)
     int Mpad;         // M rounded up to a unit
+    int fin_threads;  // threads per finalize CTA
     int nrb, ncb;     // finalize CTAs per pair: row blocks, column blocks
     size_t rowpart_off, colpart_off, losspart_off, counters_off, total_bytes;
 };
@@ -110,8 +111,10 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     p.q = (int)(p.units / g);
     p.r = (int)(p.units % g);
     p.maxslots = p.q > 0 ? cdiv(p.ups, p.q) + 1 : 1;
-    p.nrb = cdiv(N, kFinThreads);
-    p.ncb = cdiv(M, kFinThreads);
+    // every finalize CTA stages a whole cloud: larger CTAs (fewer copies) once the grid exceeds a single wave anyway
+    p.fin_threads = 2LL * B * (cdiv(N, 256) + cdiv(M, 256)) > 7LL * sm_count() ? 512 : 256;
+    p.nrb = cdiv(N, p.fin_threads);
+    p.ncb = cdiv(M, p.fin_threads);
     size_t off = 0;
     const size_t rows = (size_t)B * p.strips * p.maxslots * p.TN;
     p.rowpart_off = off;
@@ -439,7 +442,8 @@ struct FinalizeArgs {
 
 constexpr size_t kFinStageMaxBytes = 64 * 1024;    // clouds up to this size are staged
 
-__global__ void __launch_bounds__(kFinThreads, 4) chamfer_finalize_kernel(const FinalizeArgs a) {
+template <int kFinThreads>
+__global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_finalize_kernel(const FinalizeArgs a) {
     extern __shared__ __align__(16) float sCloud[];    // staged candidate cloud: p2[b] for row CTAs, p1[b] for column CTAs
     __shared__ __align__(16) float4 sPt[kFinThreads];  // (x, y, z, minimum) of the thread's point
     __shared__ int sBase[kFinThreads];                  // first candidate index to re-evaluate
@@ -763,14 +767,19 @@ int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist
     size_t fin_smem = align_up((size_t)(N > M ? N : M), 32) * 12;  // whole 32-point windows
     static const bool no_stage = getenv("FPSG_FIN_NOSTAGE") != nullptr;  // tuning override (benchmarks only)
     if (fin_smem <= kFinStageMaxBytes && !no_stage) {
-        static const cudaError_t attr_rc =
-            cudaFuncSetAttribute(chamfer_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinStageMaxBytes);
-        FPSG_CUDA_OK(attr_rc);
+        static const cudaError_t attr_rc[2] = {
+            cudaFuncSetAttribute(chamfer_finalize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinStageMaxBytes),
+            cudaFuncSetAttribute(chamfer_finalize_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinStageMaxBytes)};
+        FPSG_CUDA_OK(attr_rc[0]);
+        FPSG_CUDA_OK(attr_rc[1]);
         fa.stage = 1;
     } else {
         fin_smem = 0;
     }
-    FPSG_CUDA_OK(launch_pdl(chamfer_finalize_kernel, fgrid, dim3(kFinThreads), fin_smem, stream, fa));
+    if (pl.fin_threads == 512)
+        FPSG_CUDA_OK(launch_pdl(chamfer_finalize_kernel<512>, fgrid, dim3(512), fin_smem, stream, fa));
+    else
+        FPSG_CUDA_OK(launch_pdl(chamfer_finalize_kernel<256>, fgrid, dim3(256), fin_smem, stream, fa));
     FPSG_CUDA_OK(cudaGetLastError());
     return FPSG_OK;
 }
