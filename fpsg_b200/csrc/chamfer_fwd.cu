@@ -449,7 +449,6 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
     __shared__ int sBase[kFinThreads];                  // first candidate index to re-evaluate
     __shared__ int sFound[kFinThreads];
     __shared__ double sRed[kFinThreads / 32];
-    __shared__ bool sLast;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int b = blockIdx.y, blk = blockIdx.x;
@@ -457,6 +456,10 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
     const float* __restrict__ p2b = seg_p2(a.seg, b, a.M);
     const int TN = kSweepThreads * a.R;
     float mine = 0.f;  // this thread's distance, for the loss partial
+    // what this thread writes at the very end (after the pair's loss, see below)
+    float* out_dist = nullptr;
+    int64_t* out_idx = nullptr;
+    int out_val = 0;
     cudaTriggerProgrammaticLaunchCompletion();  // a following backward may start to launch
     // Staging: the arg-min re-evaluation reads a few candidates per point from anywhere in the other cloud -- dependent,
     // scattered global loads. The clouds are inputs, complete before the sweep (this grid's only predecessor) started, so
@@ -559,8 +562,9 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
                 if (d == m) f = min(f, o);
             }
             if (valid) {
-                if (a.dist1) a.dist1[(size_t)b * a.N + i] = m;
-                a.idx1[(size_t)b * a.N + i] = f == 0x7fffffff ? sub * kSub : sub * kSub + f;
+                if (a.dist1) out_dist = a.dist1 + (size_t)b * a.N + i;
+                out_idx = a.idx1 + (size_t)b * a.N + i;
+                out_val = f == 0x7fffffff ? sub * kSub : sub * kSub + f;
             }
         } else {
         constexpr int kBatch = 8;  // rows whose candidate loads are put in flight together (the loop is latency-bound)
@@ -598,8 +602,9 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
         }
         __syncwarp();
         if (valid && !a.stage) {
-            if (a.dist1) a.dist1[(size_t)b * a.N + i] = m;
-            a.idx1[(size_t)b * a.N + i] = sFound[tid];
+            if (a.dist1) out_dist = a.dist1 + (size_t)b * a.N + i;
+            out_idx = a.idx1 + (size_t)b * a.N + i;
+            out_val = sFound[tid];
         }
     } else {
         // ---- columns: each thread merges strips x warps ... ----
@@ -645,8 +650,9 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
                 if (d == m) f = min(f, o);
             }
             if (valid) {
-                if (a.dist2) a.dist2[(size_t)b * a.M + j] = m;
-                a.idx2[(size_t)b * a.M + j] = f == 0x7fffffff ? min(r0, last) : r0 + f;
+                if (a.dist2) out_dist = a.dist2 + (size_t)b * a.M + j;
+                out_idx = a.idx2 + (size_t)b * a.M + j;
+                out_val = f == 0x7fffffff ? min(r0, last) : r0 + f;
             }
         } else {
         constexpr int kCB = 4;  // iterations whose candidate loads are in flight together (R is a multiple of 4)
@@ -673,17 +679,17 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
         }
         __syncwarp();
         if (valid && !a.stage) {
-            if (a.dist2) a.dist2[(size_t)b * a.M + j] = m;
-            a.idx2[(size_t)b * a.M + j] = sFound[tid];
+            if (a.dist2) out_dist = a.dist2 + (size_t)b * a.M + j;
+            out_idx = a.idx2 + (size_t)b * a.M + j;
+            out_val = sFound[tid];
         }
     }
 
-    if (a.losspart) {
-        // the last CTA of the pair to arrive adds the per-CTA sums in index order, so the result does not depend on
-        // arrival order
-        if (tid == 0) sLast = ticket == (unsigned)(nblk - 1);
-        __syncthreads();
-        if (sLast && w == 0) {
+    if (a.losspart && w == 0) {
+        // The last CTA of the pair to arrive adds the per-CTA sums in index order, so the result does not depend on
+        // arrival order. Only warp 0 is involved (its lane 0 holds the ticket), and it does this BEFORE its own output
+        // stores: the fence below then has nothing outstanding to wait for, and the other warps simply finish.
+        if (__shfl_sync(0xffffffffu, ticket, 0) == (unsigned)(nblk - 1)) {
             __threadfence();
             const volatile double* lp = a.losspart + (size_t)b * nblk;
             double s1 = 0.0, s2 = 0.0;
@@ -720,6 +726,10 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
                 }
             }
         }
+    }
+    if (out_idx) {
+        if (out_dist) *out_dist = mine;
+        *out_idx = out_val;
     }
 }
 
