@@ -67,14 +67,18 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []      # (host time of arrival, fields)
+        self.windows = []   # [t_begin, t_end] of the timed regions: only samples taken inside them are reported
         self.proc = None
         self.thread = None
+
+    def mark(self, t_begin, t_end):
+        self.windows.append((t_begin, t_end))
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "25", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "10", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -85,7 +89,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 9:
-                self.rows.append(parts)
+                self.rows.append((time.perf_counter(), parts))
 
     def stop(self):
         if self.proc is None:
@@ -97,7 +101,9 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for p in self.rows:
+        inside = [p for t, p in self.rows if any(a <= t <= b + 0.012 for a, b in self.windows)]
+        total = len(self.rows)
+        for p in (inside if inside else [p for _, p in self.rows]):
             try:
                 sm.append(float(p[1]))
                 mx.append(float(p[2]))
@@ -108,7 +114,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_regions": len(inside), "samples_total": total}
 
 
 def cpu_formulation_pairs_per_s(sample_pairs: int, iters: int, threads: int | None = None):
@@ -223,6 +229,10 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi takes a few hundred ms to deliver its first sample: started ahead of the input set-up
+
     from fpsg_b200 import _lib
     import fpsg_b200
     import fpsg_b200.shims
@@ -292,14 +302,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()  # nvidia-smi needs ~0.1 s to deliver its first sample: start it ahead of the warm-up
     for i in range(args.warmup):
         step(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    tw0 = time.perf_counter()
     e0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)  # same parity/ring phase as the warm-up left it
@@ -309,6 +317,7 @@ def main():
             pending[k].wait()
             pending[k] = None
     barrier()
+    sampler.mark(tw0, time.perf_counter())
     ms = e0.elapsed_time(e1)
 
     # ---- dominant kernel alone (roofline), same ring, same stream ----
@@ -320,11 +329,13 @@ def main():
     torch.cuda.synchronize(dev)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_sweeps = max(50, min(args.steps, 400))
+    tw0 = time.perf_counter()
     s0.record(stream)
     for i in range(n_sweeps):
         sweep(5 + i)
     s1.record(stream)
     torch.cuda.synchronize(dev)
+    sampler.mark(tw0, time.perf_counter())
     sweep_us = s0.elapsed_time(s1) / n_sweeps * 1e3
 
     # ---- backward kernel alone (HBM view) ----
