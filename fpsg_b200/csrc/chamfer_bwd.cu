@@ -224,13 +224,7 @@ int chamfer_backward_launch(const SegTable& seg, const int64_t* idx1, const int6
     size_t smem = align_up((size_t)(N > M ? N : M) * 12, 16);
     static const bool no_stage = getenv("FPSG_BWD_NOSTAGE") != nullptr;  // tuning override (benchmarks only)
     bool stage = smem <= kBwdStageMaxBytes && !no_stage;
-    if (stage) {
-        static const cudaError_t attr_rc =
-            cudaFuncSetAttribute(chamfer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdStageMaxBytes);
-        FPSG_CUDA_OK(attr_rc);
-    } else {
-        smem = 0;
-    }
+    if (!stage) smem = 0;  // (staged: at most 32 KB + 10 KB static, below the 48 KB that would need an opt-in)
     FPSG_CUDA_OK(launch_pdl(chamfer_bwd_kernel, grid, dim3(kBwdThreads), smem, stream, seg, s1, s2, uniform, gtotal, stage));
     return FPSG_OK;
 }

@@ -777,11 +777,14 @@ int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist
     size_t fin_smem = align_up((size_t)(N > M ? N : M), 32) * 12;  // whole 32-point windows
     static const bool no_stage = getenv("FPSG_FIN_NOSTAGE") != nullptr;  // tuning override (benchmarks only)
     if (fin_smem <= kFinStageMaxBytes && !no_stage) {
-        static const cudaError_t attr_rc[2] = {
-            cudaFuncSetAttribute(chamfer_finalize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinStageMaxBytes),
-            cudaFuncSetAttribute(chamfer_finalize_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinStageMaxBytes)};
-        FPSG_CUDA_OK(attr_rc[0]);
-        FPSG_CUDA_OK(attr_rc[1]);
+        // more than 48 KB of shared memory per CTA (static + dynamic) needs an opt-in; it is per device, so it is repeated
+        // per launch (as the kNN launches do) -- the c1 shapes (24 KB) never get here
+        if (fin_smem > 32 * 1024) {
+            if (pl.fin_threads == 512)
+                FPSG_CUDA_OK(cudaFuncSetAttribute(chamfer_finalize_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinStageMaxBytes));
+            else
+                FPSG_CUDA_OK(cudaFuncSetAttribute(chamfer_finalize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinStageMaxBytes));
+        }
         fa.stage = 1;
     } else {
         fin_smem = 0;
