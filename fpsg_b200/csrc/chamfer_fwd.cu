@@ -60,7 +60,7 @@ struct ChamferPlan {
     int Mpad;         // M rounded up to a unit
     int fin_threads;  // threads per finalize CTA
     int nrb, ncb;     // finalize CTAs per pair: row blocks, column blocks
-    size_t rowpart_off, colpart_off, losspart_off, counters_off, total_bytes;
+    size_t rowmin_off, rowsub_off, colpart_off, losspart_off, counters_off, total_bytes;
 };
 
 static int g_sm_count = 0;
@@ -117,8 +117,10 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     p.ncb = cdiv(M, p.fin_threads);
     size_t off = 0;
     const size_t rows = (size_t)B * p.strips * p.maxslots * p.TN;
-    p.rowpart_off = off;
-    off += align_up(rows * sizeof(u64), 256);
+    p.rowmin_off = off;
+    off += align_up(rows * sizeof(float), 256);
+    p.rowsub_off = off;
+    off += align_up(rows * sizeof(int), 256);
     p.colpart_off = off;
     off += align_up((size_t)B * p.strips * kSweepWarps * p.Mpad * sizeof(u64), 256);
     p.losspart_off = off;
@@ -132,8 +134,9 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
 struct SweepArgs {
     SegTable seg;   // the clouds: p1 (B,N,3), p2 (B,M,3), possibly in several separately allocated segments
     int N, M, strips, ups, q, r, maxslots, Mpad;
-    u64* rowpart;   // [B*strips][maxslots][TN]   (row partial minimum bits << 32) | sub-block that produced it;
-                    //                            one slot per CTA that covered the (pair, strip)
+    float* rowmin;  // [B*strips][maxslots][TN]   row partial minima, one slot per CTA that covered the (pair, strip) ...
+    int* rowsub;    // [B*strips][maxslots][TN]   ... and the sub-block that produced each (two arrays: the finalize kernel
+                    //                            merges the 4-byte minima and then reads one sub-block index per row)
     u64* colpart;   // [B*strips][4 warps][Mpad]  (min bits << 32) | ballot of lanes attaining it
     unsigned* counters;  // [B + 1] arrival counters of the finalize kernel's loss reductions; zeroed here (or nullptr)
     int B;
@@ -406,11 +409,14 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
 
         // last piece of this (pair, strip) for this CTA: flush the row partials
         if (nleft == 0 || nbs != bs) {
-            ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.rowpart + ((size_t)bs * a.maxslots + slot) * (kSweepThreads * R) + tid * R);
+            const size_t o = ((size_t)bs * a.maxslots + slot) * (kSweepThreads * R) + tid * R;
+            float4* dm = reinterpret_cast<float4*>(a.rowmin + o);
+            int4* ds = reinterpret_cast<int4*>(a.rowsub + o);
 #pragma unroll
-            for (int k = 0; k < R; k += 2)
-                dst[k >> 1] = make_ulonglong2(((u64)__float_as_uint(best[k]) << 32) | (unsigned)sSubIdx[k][tid],
-                                              ((u64)__float_as_uint(best[k + 1]) << 32) | (unsigned)sSubIdx[k + 1][tid]);
+            for (int k = 0; k < R; k += 4) {
+                dm[k >> 2] = make_float4(best[k], best[k + 1], best[k + 2], best[k + 3]);
+                ds[k >> 2] = make_int4(sSubIdx[k][tid], sSubIdx[k + 1][tid], sSubIdx[k + 2][tid], sSubIdx[k + 3][tid]);
+            }
         }
         bs = nbs;
         cu = ncu;
@@ -424,7 +430,8 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
 struct FinalizeArgs {
     SegTable seg;
     int N, M, R, strips, ups, q, r, maxslots, Mpad;
-    const u64* rowpart;
+    const float* rowmin;
+    const int* rowsub;
     const u64* colpart;
     float* dist1;
     float* dist2;
@@ -516,26 +523,33 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             const int bs = b * a.strips + strip;
             const int u0 = bs * a.ups;
             const int g0 = cta_of_unit(u0, a.q, a.r), g1 = cta_of_unit(u0 + a.ups - 1, a.q, a.r);
-            // the keys order by (minimum, sub-block): their u64 minimum is the reference's strict-'<' ascending scan.
-            // All loads of the merge are issued together (one L2 round trip); slots past nsl hold stale data.
-            const u64* rp = a.rowpart + (size_t)bs * a.maxslots * TN + within;
+            // Slots are in ascending column order, so the first slot (strict '<') that attains the minimum holds the
+            // lowest sub-block among equal minima: the reference's strict-'<' ascending scan at sub-block granularity.
+            // All 4-byte minima of a batch are in flight together (one L2 round trip; slots past the last one re-read
+            // it), then one dependent load fetches the winner's sub-block index.
+            const size_t ro = (size_t)bs * a.maxslots * TN + within;
+            const float* rm = a.rowmin + ro;
             const int nsl = g1 - g0 + 1;
-            u64 key = ~0ull;
-            constexpr int kSlotBatch = 12;  // loads in flight together
+            int ms = 0;
+            constexpr int kSlotBatch = 24;
             for (int s0 = 0; s0 < nsl; s0 += kSlotBatch) {
-                u64 v[kSlotBatch];
+                float v[kSlotBatch];
 #pragma unroll
-                for (int s = 0; s < kSlotBatch; ++s) v[s] = s0 + s < nsl ? rp[(size_t)(s0 + s) * TN] : ~0ull;
+                for (int s = 0; s < kSlotBatch; ++s) v[s] = __ldcg(rm + (size_t)min(s0 + s, nsl - 1) * TN);
                 if (s0 == 0) {
                     ax = __ldg(p1b + 3 * i);
                     ay = __ldg(p1b + 3 * i + 1);
                     az = __ldg(p1b + 3 * i + 2);
                 }
 #pragma unroll
-                for (int s = 0; s < kSlotBatch; ++s) key = v[s] < key ? v[s] : key;
+                for (int s = 0; s < kSlotBatch; ++s) {
+                    if (v[s] < m) {
+                        m = v[s];
+                        ms = min(s0 + s, nsl - 1);
+                    }
+                }
             }
-            m = __uint_as_float((unsigned)(key >> 32));
-            sub = (int)(unsigned)key;
+            sub = __ldcg(a.rowsub + ro + (size_t)ms * TN);
             mine = m;
         }
         stage_cloud();
@@ -755,12 +769,13 @@ int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist
         return fail(FPSG_EWORKSPACE, "chamfer: workspace of %zu bytes required, %zu given", pl.total_bytes, ws ? ws_bytes : (size_t)0);
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(FPSG_EWORKSPACE, "chamfer: workspace must be 256-byte aligned");
     char* base = static_cast<char*>(ws);
-    u64* rowpart = reinterpret_cast<u64*>(base + pl.rowpart_off);
+    float* rowmin = reinterpret_cast<float*>(base + pl.rowmin_off);
+    int* rowsub = reinterpret_cast<int*>(base + pl.rowsub_off);
     u64* colpart = reinterpret_cast<u64*>(base + pl.colpart_off);
     double* losspart = loss ? reinterpret_cast<double*>(base + pl.losspart_off) : nullptr;
     unsigned* counters = loss ? reinterpret_cast<unsigned*>(base + pl.counters_off) : nullptr;
 
-    const SweepArgs sa{seg, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart, counters, B};
+    const SweepArgs sa{seg, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowmin, rowsub, colpart, counters, B};
     const dim3 sgrid((unsigned)pl.grid), sblock(kSweepThreads);
     if (pl.R == 16 && pl.packed)
         FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<16, true>, sgrid, sblock, 0, stream, sa));
@@ -771,7 +786,7 @@ int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist
     else
         FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<4, false>, sgrid, sblock, 0, stream, sa));
     if (sweep_only) return FPSG_OK;
-    FinalizeArgs fa{seg, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowpart, colpart,
+    FinalizeArgs fa{seg, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowmin, rowsub, colpart,
                           dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb, totals, B, 0};
     const dim3 fgrid((unsigned)(pl.nrb + pl.ncb), (unsigned)B);
     size_t fin_smem = align_up((size_t)(N > M ? N : M), 32) * 12;  // whole 32-point windows
