@@ -42,6 +42,7 @@ constexpr int kSweepThreads = 128;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kUnit = 16;           // columns per scheduling unit
 constexpr int kSub = 32;            // columns per shared-memory sub-block (2 units)
+static_assert(kSub == 32, "the finalize kernel permutes a row's window with lane ^ c");
 
 
 // resident sweep CTAs per SM (register-limited): the persistent grid is this times the SM count
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             for (int s0 = 0; s0 < nsl; s0 += kSlotBatch) {
                 float v[kSlotBatch];
 #pragma unroll
-                for (int s = 0; s < kSlotBatch; ++s) v[s] = __ldcg(rm + (size_t)min(s0 + s, nsl - 1) * TN);
+                for (int s = 0; s < kSlotBatch; ++s) v[s] = __ldcg(rm + (unsigned)(min(s0 + s, nsl - 1) * TN));  // < maxslots * TN: 32 bits
                 if (s0 == 0) {
                     ax = __ldg(p1b + 3 * i);
                     ay = __ldg(p1b + 3 * i + 1);
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
                     }
                 }
             }
-            sub = __ldcg(a.rowsub + ro + (size_t)ms * TN);
+            sub = __ldcg(a.rowsub + ro + (unsigned)(ms * TN));
             mine = m;
         }
         stage_cloud();
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             int f = 0x7fffffff;
 #pragma unroll 8
             for (int c = 0; c < kSub; ++c) {
-                const int o = (lane + c) & (kSub - 1);
+                const int o = lane ^ c;  // a lane-dependent permutation of the window (kSub == 32)
                 const float d = sqdist(ax, ay, az, win[3 * o], win[3 * o + 1], win[3 * o + 2]);
                 if (d == m) f = min(f, o);
             }
@@ -667,7 +668,7 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             int f = 0x7fffffff;
 #pragma unroll 4
             for (int c = 0; c < R; ++c) {
-                const int o = (lane + c) & (R - 1);
+                const int o = (lane ^ c) & (R - 1);
                 const float d = sqdist(qx, qy, qz, win[3 * o], win[3 * o + 1], win[3 * o + 2]);
                 if (d == m) f = min(f, o);
             }
