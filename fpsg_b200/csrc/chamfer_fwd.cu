@@ -149,14 +149,14 @@ __device__ __forceinline__ int cta_of_unit(int u, int q, int r) {
     return u < cut ? u / (q + 1) : r + (u - cut) / q;
 }
 
-// Arrival counters of the finalize kernel's reductions: the arriving thread's earlier stores are released by the
-// increment itself (atom.release: no full MEMBAR.SC in front of it), the last arriver acquires before it reads.
-__device__ __forceinline__ unsigned arrive_release(unsigned* counter) {
+// Arrival counters of the finalize kernel's reductions. The increment is an acq_rel atomic: it releases the arriving
+// thread's earlier stores (no MEMBAR.SC in front of it) and, for the last arriver, acquires everybody else's -- at the
+// place where the atomic is issued, i.e. early and off the critical path, instead of a fence in front of the final loads.
+__device__ __forceinline__ unsigned arrive_acq_rel(unsigned* counter) {
     unsigned old;
-    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
     return old;
 }
-__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_min_f32(float v) {
     float m;
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             double s = 0.0;
             for (int q = 0; q < kFinThreads / 32; ++q) s += sRed[q];
             a.losspart[(size_t)b * nblk + blk] = s;
-            ticket = arrive_release(a.counters + b);  // publishes the partial sum stored above
+            ticket = arrive_acq_rel(a.counters + b);  // publishes the partial sum stored above
         }
     };
 
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
         // arrival order. Only warp 0 is involved (its lane 0 holds the ticket), and it does this BEFORE its own output
         // stores: the fence below then has nothing outstanding to wait for, and the other warps simply finish.
         if (__shfl_sync(0xffffffffu, ticket, 0) == (unsigned)(nblk - 1)) {
-            fence_acquire();
+            __syncwarp();  // lane 0's acquire (its atomic) is ordered before the other lanes' loads below
             const volatile double* lp = a.losspart + (size_t)b * nblk;
             double s1 = 0.0, s2 = 0.0;
             for (int q = lane; q < a.nrb; q += 32) s1 += lp[q];
@@ -729,10 +729,10 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
                 // losses in index order, per segment, in double -- again independent of arrival order
                 bool last = false;
                 if (lane == 0) {
-                    last = arrive_release(a.counters + a.B) == (unsigned)(a.B - 1);  // publishes loss[b]
+                    last = arrive_acq_rel(a.counters + a.B) == (unsigned)(a.B - 1);  // publishes loss[b]
                 }
                 if (__shfl_sync(0xffffffffu, last, 0)) {
-                    fence_acquire();
+                    __syncwarp();
                     const volatile float* lv = a.loss;
                     double total = 0.0;
                     for (int sg = 0; sg < a.seg.n; ++sg) {
