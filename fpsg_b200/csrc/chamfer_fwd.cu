@@ -468,7 +468,10 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
     __shared__ double sRed[kFinThreads / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int b = blockIdx.y, blk = blockIdx.x;
+    // pair-fastest grid: CTAs are dispatched block row by block row, i.e. all row blocks (the long ones: ~20 partials per
+    // row) of all pairs before any column block. The CTAs that only become resident when the last sweep CTAs retire -- and
+    // whose cloud copy is still in flight when the dependency wait ends -- are then the short column blocks.
+    const int b = blockIdx.x, blk = blockIdx.y;
     const float* __restrict__ p1b = seg_p1(a.seg, b, a.N);
     const float* __restrict__ p2b = seg_p2(a.seg, b, a.M);
     const int TN = kSweepThreads * a.R;
@@ -796,7 +799,8 @@ int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist
     if (sweep_only) return FPSG_OK;
     FinalizeArgs fa{seg, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowmin, rowsub, colpart,
                           dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb, totals, B, 0};
-    const dim3 fgrid((unsigned)(pl.nrb + pl.ncb), (unsigned)B);
+    if (pl.nrb + pl.ncb > 65535) return fail(FPSG_EINVAL, "chamfer: N + M too large for one call");
+    const dim3 fgrid((unsigned)B, (unsigned)(pl.nrb + pl.ncb));
     size_t fin_smem = align_up((size_t)(N > M ? N : M), 32) * 12;  // whole 32-point windows
     static const bool no_stage = getenv("FPSG_FIN_NOSTAGE") != nullptr;  // tuning override (benchmarks only)
     if (fin_smem <= kFinStageMaxBytes && !no_stage) {
