@@ -114,6 +114,10 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     p.maxslots = p.q > 0 ? cdiv(p.ups, p.q) + 1 : 1;
     // every finalize CTA stages a whole cloud: larger CTAs (fewer copies) once the grid exceeds a single wave anyway
     p.fin_threads = 2LL * B * (cdiv(N, 256) + cdiv(M, 256)) > 7LL * sm_count() ? 512 : 256;
+    if (const char* e = getenv("FPSG_FIN_THREADS")) {  // tuning override (benchmarks only): 256 or 512
+        const int v = atoi(e);
+        if (v == 256 || v == 512) p.fin_threads = v;
+    }
     p.nrb = cdiv(N, p.fin_threads);
     p.ncb = cdiv(M, p.fin_threads);
     size_t off = 0;
