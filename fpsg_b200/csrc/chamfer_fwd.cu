@@ -9,21 +9,24 @@
 //   sweep kernel    : persistent grid (a multiple of the SM count). The work of the whole batch is cut into
 //                     units of (pair, row strip, 16 columns) and every CTA takes an equal contiguous run of
 //                     units, so all SMs finish together whatever B, N, M are. CTA = 128 threads; thread t keeps R
-//                     consecutive rows (p1 points) in registers and streams <=64-column sub-blocks of p2
+//                     consecutive rows (p1 points) in registers and streams 32-column sub-blocks of p2
 //                     through a per-warp shared-memory tile (AoS, three broadcast LDS.128 per 4 columns; the next
 //                     sub-block is prefetched into registers during the current one; no CTA-wide barrier).
 //                     Row direction : best[k] = min3(best[k], d, d') -- value only; once per sub-block the
 //                                     thread notes (in shared memory) which sub-block last lowered best[k].
 //                     Column direction: per column the thread's minimum over its R rows, then one warp-wide
 //                                     CREDUX.MIN.F32 + ballot gives (warp minimum, lanes attaining it); lane 0
-//                                     parks that in shared memory and the warp writes its 64 results coalesced.
+//                                     parks that in shared memory and the warp writes its 32 results coalesced.
 //                     There is no arg-min bookkeeping per distance and no CTA-wide reduction.
 //   finalize kernel : merges the partial minima (rows: over the CTAs that covered the row's strip; columns:
 //                     over strips x warps) and recovers the arg-min exactly by re-evaluating the few candidates
-//                     the partials point at (the 64 columns of the winning sub-block for a row, the R rows of
+//                     the partials point at (the 32 columns of the winning sub-block for a row, the R rows of
 //                     the winning thread for a column) with the same FP32 instruction sequence, taking the
 //                     lowest index whose distance equals the minimum bit-for-bit. That reproduces the
-//                     reference's strict-'<' ascending scan (lowest index wins ties).
+//                     reference's strict-'<' ascending scan (lowest index wins ties). For clouds up to 64 KB the
+//                     candidates' cloud is staged in shared memory (cp.async issued ahead of the dependency
+//                     wait) and every thread scans its own window there; the grid is pair-fastest so that the
+//                     row blocks (the long ones) are dispatched before the column blocks.
 //   loss (optional) : w1*mean(dist1) + w2*mean(dist2) per pair -- the reduction glue of few_shot.py:110 / kaolin's
 //                     chamfer_distance -- folded into the finalize kernel: per-CTA double sums, added in index
 //                     order by whichever CTA of the pair arrives last (deterministic, no extra launch).
