@@ -1,5 +1,6 @@
-"""c1 step anatomy through the C ABI (development aid): sweep alone, forward (sweep + finalize), backward alone and the
-chained step, over the same ring of HBM-resident inputs bench.py uses. Usage: step_c1.py [B N M]"""
+"""c1 step anatomy through the C ABI (development aid): sweep alone, forward (sweep + finalize), backward alone, the
+chained three-kernel step and the fused step (sweep + finish kernel), over the same ring of HBM-resident inputs
+bench.py uses. Usage: step_c1.py [B N M]"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -30,6 +31,9 @@ def bwd(i):
     _lib.check(L.fpsg_chamfer_loss_bwd(a, b, o[1], o[2], o[4], 1.0, 1.0, B, N, M, o[5], None, None, 0, st))
 def step(i):
     fwd(i); bwd(i)
+def fused(i):
+    a, b = ptrs[i % sets]
+    _lib.check(L.fpsg_chamfer_loss_fwd_bwd(a, b, B, N, M, 1.0, 1.0, None, o[0], None, None, o[1], o[2], o[5], None, o[3], nb, st))
 
 def t(fn, it):
     for i in range(20): fn(i)
@@ -46,4 +50,4 @@ def t(fn, it):
 it = 400 if B * N * M < 5e9 else 20
 fwd(0); torch.cuda.synchronize()
 print(json.dumps({"B": B, "N": N, "M": M, "sweep_us": t(sweep, it), "fwd_us": t(fwd, it), "bwd_us": t(bwd, it), "step_us": t(step, it),
-                  "env": {k: v for k, v in os.environ.items() if k.startswith("FPSG_")}}))
+                  "fused_step_us": t(fused, it), "env": {k: v for k, v in os.environ.items() if k.startswith("FPSG_")}}))

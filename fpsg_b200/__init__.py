@@ -4,11 +4,12 @@ forward/backward and the DGCNN kNN graph, behind the reference's own call surfac
     from fpsg_b200 import chamfer_distance, chamfer_loss, sided_distance, knn
     import fpsg_b200.shims; fpsg_b200.shims.install()   # makes the reference source run unchanged
 """
-from .chamfer import chamfer_distance, chamfer_loss, chamfer_loss_multi, sided_distance
+from .chamfer import (chamfer_distance, chamfer_loss, chamfer_loss_and_grad, chamfer_loss_multi, chamfer_loss_multi_and_grad,
+                      sided_distance)
 from .graph_feature import get_graph_feature
 from .knn import knn
 from .pointcloud_io import normalize_point_clouds, ply_reader
 
-__all__ = ["chamfer_distance", "chamfer_loss", "chamfer_loss_multi", "sided_distance", "knn", "get_graph_feature", "ply_reader",
+__all__ = ["chamfer_distance", "chamfer_loss", "chamfer_loss_and_grad", "chamfer_loss_multi", "chamfer_loss_multi_and_grad", "sided_distance", "knn", "get_graph_feature", "ply_reader",
            "normalize_point_clouds"]
 __version__ = "0.1.0"

@@ -54,6 +54,12 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_chamfer_multi_loss_fwd.argtypes = [segp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, c_size_t, vp]
     L.fpsg_chamfer_multi_loss_bwd.restype = c_int
     L.fpsg_chamfer_multi_loss_bwd.argtypes = [segp, c_int, vp, vp, vp, c_float, c_float, c_int, c_int, vp]
+    L.fpsg_chamfer_loss_fwd_bwd.restype = c_int
+    L.fpsg_chamfer_loss_fwd_bwd.argtypes = [vp, vp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp]
+    L.fpsg_chamfer_multi_loss_fwd_bwd.restype = c_int
+    L.fpsg_chamfer_multi_loss_fwd_bwd.argtypes = [segp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, vp, c_size_t, vp]
+    L.fpsg_chamfer_ws_diag_offset.restype = c_size_t
+    L.fpsg_chamfer_ws_diag_offset.argtypes = [c_int, c_int, c_int]
     L.fpsg_knn_workspace_bytes.restype = c_size_t
     L.fpsg_knn_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     L.fpsg_knn_fwd.restype = c_int

@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfpsg_b200.so")
-SOURCES = ["api.cu", "chamfer_fwd.cu", "chamfer_bwd.cu", "knn.cu", "edge_feature.cu", "pointcloud_io.cu"]
+SOURCES = ["api.cu", "chamfer_fwd.cu", "chamfer_finish.cu", "chamfer_bwd.cu", "knn.cu", "edge_feature.cu", "pointcloud_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-cudart", "static", "-diag-suppress", "550"]
 
@@ -32,7 +32,8 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    tuning = ["-DFPSG_TUNING"] if os.environ.get("FPSG_BUILD_TUNING") else []  # FPSG_* ablation switches (bench_micro/) compiled in
+    cmd = [_nvcc()] + NVCC_FLAGS + tuning + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -67,6 +67,7 @@ class _device_guard:
 
 
 _WS_BYTES = {}  # (B, N, M) -> workspace size; the query is pure arithmetic, cache it
+_DIAG = {"keep": False, "last": None}  # tests: keep the last workspace so that its diagnostic counter can be read
 
 
 def _workspace(B: int, N: int, M: int, device) -> tuple[torch.Tensor, int]:
@@ -76,7 +77,26 @@ def _workspace(B: int, N: int, M: int, device) -> tuple[torch.Tensor, int]:
         nbytes = int(_lib.lib().fpsg_chamfer_fwd_workspace_bytes(B, N, M))
         _WS_BYTES[key] = nbytes
     # a fresh caching-allocator block per call: safe under multi-stream use, and the allocator makes it cheap
-    return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device), nbytes
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+    if _DIAG["keep"]:
+        _DIAG["last"] = (ws, B, N, M)
+    return ws, nbytes
+
+
+def diag_keep_workspaces(on: bool = True) -> None:
+    """Test hook: keep a reference to the workspace of the most recent Chamfer forward (see ``diag_mismatches``)."""
+    _DIAG["keep"] = bool(on)
+    _DIAG["last"] = None
+
+
+def diag_mismatches() -> int:
+    """The diagnostic counter of the most recent forward's workspace (include/fpsg_b200.h, fpsg_chamfer_ws_diag_offset):
+    arg-min recoveries that found no candidate bit-equal to the merged minimum. Must be 0. Synchronises."""
+    if _DIAG["last"] is None:
+        raise RuntimeError("no workspace kept: call diag_keep_workspaces() before the forward")
+    ws, B, N, M = _DIAG["last"]
+    off = int(_lib.lib().fpsg_chamfer_ws_diag_offset(B, N, M))
+    return int(ws[off:off + 4].view(torch.int32).item())
 
 
 def _forward(p1: torch.Tensor, p2: torch.Tensor):
@@ -272,6 +292,84 @@ def chamfer_loss_multi(pairs, weights=None, w1: float = 1.0, w2: float = 1.0):
         raise RuntimeError("one weight per pair of clouds is required")
     flat = [t for pr in pairs for t in pr]
     return _ChamferLossMulti.apply(float(w1), float(w2), tuple(weights), *flat)
+
+
+def chamfer_loss_and_grad(p1: torch.Tensor, p2: torch.Tensor, w1: float = 1.0, w2: float = 1.0, gloss: torch.Tensor | None = None,
+                          need_gp1: bool = True, need_gp2: bool = False, return_indices: bool = False):
+    """Forward AND backward of ``chamfer_loss(p1, p2, w1, w2)`` in one fused launch chain, for a loss whose upstream
+    gradient is known up front -- the reference's training step, ``pc_metric(a, b).sum()`` followed by
+    ``ttl_loss.backward()`` (src/models/few_shot.py:110,117, src/trainNetwork.py:144), where that gradient is a constant.
+
+    ``gloss`` (B,) is the upstream gradient of the per-pair loss (``None`` = ones, the ``.sum()`` case). Returns
+    ``(loss (B,), gp1 or None, gp2 or None)`` (plus ``idx1, idx2`` with ``return_indices``). Not recorded by autograd:
+    feed ``gp1`` to ``p1.backward(gp1)`` (or use ``chamfer_loss`` when the upstream gradient is not known in advance)."""
+    p1, p2 = _check_clouds(p1.detach(), p2.detach())
+    B, N = p1.shape[0], p1.shape[1]
+    M = p2.shape[1]
+    dev = p1.device
+    idx = torch.empty((B * (N + M),), dtype=torch.int64, device=dev)
+    loss = torch.empty((B,), dtype=torch.float32, device=dev)
+    gp1 = torch.empty_like(p1) if need_gp1 else None
+    gp2 = torch.empty_like(p2) if need_gp2 else None
+    if gloss is not None:
+        if gloss.shape != (B,) or gloss.device != dev:
+            raise RuntimeError(f"gloss must have shape ({B},) on {dev}, got {tuple(gloss.shape)} on {gloss.device}")
+        gloss = gloss.detach().to(torch.float32).contiguous()
+    if B > 0:
+        with _device_guard(dev):
+            ws, nbytes = _workspace(B, N, M, dev)
+            ip = idx.data_ptr()
+            _lib.check(_lib.lib().fpsg_chamfer_loss_fwd_bwd(
+                p1.data_ptr(), p2.data_ptr(), B, N, M, float(w1), float(w2), gloss.data_ptr() if gloss is not None else None,
+                loss.data_ptr(), None, None, ip, ip + 8 * B * N, gp1.data_ptr() if need_gp1 else None,
+                gp2.data_ptr() if need_gp2 else None, ws.data_ptr(), nbytes, _stream_ptr(dev)))
+    if return_indices:
+        return loss, gp1, gp2, idx[:B * N].view(B, N), idx[B * N:].view(B, M)
+    return loss, gp1, gp2
+
+
+def chamfer_loss_multi_and_grad(pairs, weights=None, w1: float = 1.0, w2: float = 1.0, gtotal: torch.Tensor | None = None,
+                                need_grad=None):
+    """``chamfer_loss_multi`` forward and backward in one fused launch chain (see ``chamfer_loss_and_grad``):
+    ``gtotal`` = device scalar, the upstream gradient of the weighted total (``None`` = 1, ``ttl_loss.backward()``);
+    ``need_grad`` = one ``(need_gp1, need_gp2)`` per pair of clouds (default ``(True, False)``: the reference's ground
+    truth never needs a gradient). Returns ``(total, sums, loss, grads)`` with ``grads[s] = (gp1 or None, gp2 or None)``."""
+    pairs = [_check_clouds(a.detach(), b.detach()) for a, b in pairs]
+    nseg = len(pairs)
+    if not 1 <= nseg <= _lib.MAX_SEGMENTS:
+        raise RuntimeError(f"need 1..{_lib.MAX_SEGMENTS} pairs of clouds, got {nseg}")
+    weights = [1.0] * nseg if weights is None else [float(w) for w in weights]
+    need_grad = [(True, False)] * nseg if need_grad is None else list(need_grad)
+    if len(weights) != nseg or len(need_grad) != nseg:
+        raise RuntimeError("one weight and one need_grad entry per pair of clouds is required")
+    N, M = pairs[0][0].shape[1], pairs[0][1].shape[1]
+    dev = pairs[0][0].device
+    for a, b in pairs:
+        if a.shape[1] != N or b.shape[1] != M:
+            raise RuntimeError(f"all segments must share N and M: got {(a.shape[1], b.shape[1])} vs {(N, M)}")
+        if a.device != dev:
+            raise RuntimeError("all segments must live on the same device")
+    Btot = sum(a.shape[0] for a, _ in pairs)
+    segs = (_lib.ChamferSegment * nseg)()
+    grads = []
+    for s, (a, b) in enumerate(pairs):
+        g1 = torch.empty_like(a) if need_grad[s][0] else None
+        g2 = torch.empty_like(b) if need_grad[s][1] else None
+        grads.append((g1, g2))
+        segs[s].p1, segs[s].p2 = a.data_ptr(), b.data_ptr()
+        segs[s].gp1 = g1.data_ptr() if g1 is not None else None
+        segs[s].gp2 = g2.data_ptr() if g2 is not None else None
+        segs[s].batch, segs[s].weight = a.shape[0], weights[s]
+    idx = torch.empty((Btot * (N + M),), dtype=torch.int64, device=dev)
+    out = torch.empty((1 + nseg + Btot,), dtype=torch.float32, device=dev)
+    if gtotal is not None:
+        gtotal = gtotal.detach().to(torch.float32).reshape(()).contiguous()
+    with _device_guard(dev):
+        ws, nbytes = _workspace(Btot, N, M, dev) if Btot > 0 else (None, 0)
+        _lib.check(_lib.lib().fpsg_chamfer_multi_loss_fwd_bwd(
+            segs, nseg, N, M, float(w1), float(w2), gtotal.data_ptr() if gtotal is not None else None, out[1 + nseg:].data_ptr(),
+            out.data_ptr(), idx.data_ptr(), idx[Btot * N:].data_ptr(), ws.data_ptr() if ws is not None else None, nbytes, _stream_ptr(dev)))
+    return out[0], out[1:1 + nseg], out[1 + nseg:], grads
 
 
 def chamfer_distance(p1: torch.Tensor, p2: torch.Tensor):

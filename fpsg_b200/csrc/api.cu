@@ -22,7 +22,13 @@ int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist
                            int64_t* idx2, float* loss, float* totals, float w1, float w2, void* ws, size_t ws_bytes,
                            cudaStream_t stream, bool sweep_only);
 int chamfer_backward_launch(const SegTable& seg, const int64_t* idx1, const int64_t* idx2, const float* g1, const float* g2,
-                            bool uniform, const float* gtotal, float w1, float w2, int B, int N, int M, cudaStream_t stream);
+                            bool uniform, bool multi, const float* gtotal, float w1, float w2, int B, int N, int M, cudaStream_t stream);
+size_t chamfer_diag_offset(int B, int N, int M);
+// pieces of the forward (chamfer_fwd.cu) and the fused finalize + backward kernel (chamfer_finish.cu)
+struct ChamferPlan;
+int chamfer_fwd_bwd_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, float* loss,
+                           float* totals, float w1, float w2, const float* gloss, const float* gtotal, bool multi, void* ws, size_t ws_bytes,
+                           cudaStream_t stream, int mode);
 
 // host array of segments -> the table the kernels index; returns the total number of pairs or a negative error
 static int make_seg_table(const fpsg_chamfer_segment_t* segs, int nseg, SegTable* out) {
@@ -111,7 +117,7 @@ size_t fpsg_chamfer_bwd_workspace_bytes(int, int, int) { return 0; }
 int fpsg_chamfer_bwd(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2, const float* g1,
                      const float* g2, int B, int N, int M, float* gp1, float* gp2, void*, size_t, fpsg_stream_t stream) {
     if (B > 0 && (gp1 || gp2) && (!p1 || !p2)) return fail(FPSG_EINVAL, "chamfer_bwd: null input pointer");
-    return chamfer_backward_launch(single_segment(p1, p2, gp1, gp2, B), idx1, idx2, g1, g2, false, nullptr, 1.f, 1.f, B, N, M,
+    return chamfer_backward_launch(single_segment(p1, p2, gp1, gp2, B), idx1, idx2, g1, g2, false, false, nullptr, 1.f, 1.f, B, N, M,
                                    static_cast<cudaStream_t>(stream));
 }
 
@@ -127,7 +133,8 @@ int fpsg_chamfer_loss_bwd(const float* p1, const float* p2, const int64_t* idx1,
                           float w1, float w2, int B, int N, int M, float* gp1, float* gp2, void*, size_t,
                           fpsg_stream_t stream) {
     if (B > 0 && (gp1 || gp2) && (!p1 || !p2)) return fail(FPSG_EINVAL, "chamfer_bwd: null input pointer");
-    return chamfer_backward_launch(single_segment(p1, p2, gp1, gp2, B), idx1, idx2, gloss, gloss, true, nullptr, w1, w2, B, N, M,
+    if (B > 0 && (gp1 || gp2) && !gloss) return fail(FPSG_EINVAL, "chamfer_loss_bwd: null gloss");
+    return chamfer_backward_launch(single_segment(p1, p2, gp1, gp2, B), idx1, idx2, gloss, gloss, true, false, nullptr, w1, w2, B, N, M,
                                    static_cast<cudaStream_t>(stream));
 }
 
@@ -153,8 +160,34 @@ int fpsg_chamfer_multi_loss_bwd(const fpsg_chamfer_segment_t* segs_host, int nse
     const int B = make_seg_table(segs_host, nseg, &t);
     if (B < 0) return B;
     if (!gtotal) return fail(FPSG_EINVAL, "chamfer_multi_loss_bwd: null gtotal");
-    return chamfer_backward_launch(t, idx1, idx2, nullptr, nullptr, true, gtotal, w1, w2, B, N, M, static_cast<cudaStream_t>(stream));
+    return chamfer_backward_launch(t, idx1, idx2, nullptr, nullptr, true, true, gtotal, w1, w2, B, N, M, static_cast<cudaStream_t>(stream));
 }
+
+int fpsg_chamfer_loss_fwd_bwd(const float* p1, const float* p2, int B, int N, int M, float w1, float w2, const float* gloss, float* loss,
+                              float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, float* gp1, float* gp2, void* ws, size_t ws_bytes,
+                              fpsg_stream_t stream) {
+    if (B > 0 && !loss) return fail(FPSG_EINVAL, "chamfer_loss_fwd_bwd: null loss");
+    return chamfer_fwd_bwd_launch(single_segment(p1, p2, gp1, gp2, B), B, N, M, dist1, dist2, idx1, idx2, loss, nullptr, w1, w2, gloss, nullptr,
+                                  false, ws, ws_bytes, static_cast<cudaStream_t>(stream), 0);
+}
+
+int fpsg_chamfer_multi_loss_fwd_bwd(const fpsg_chamfer_segment_t* segs_host, int nseg, int N, int M, float w1, float w2, const float* gtotal,
+                                    float* loss, float* totals, int64_t* idx1, int64_t* idx2, void* ws, size_t ws_bytes,
+                                    fpsg_stream_t stream) {
+    SegTable t;
+    const int B = make_seg_table(segs_host, nseg, &t);
+    if (B < 0) return B;
+    if (!totals) return fail(FPSG_EINVAL, "chamfer_multi_loss_fwd_bwd: null totals");
+    if (B == 0) {
+        FPSG_CUDA_OK(cudaMemsetAsync(totals, 0, sizeof(float) * (size_t)(1 + nseg), static_cast<cudaStream_t>(stream)));
+        return FPSG_OK;
+    }
+    if (!loss) return fail(FPSG_EINVAL, "chamfer_multi_loss_fwd_bwd: null loss");
+    return chamfer_fwd_bwd_launch(t, B, N, M, nullptr, nullptr, idx1, idx2, loss, totals, w1, w2, nullptr, gtotal, true, ws, ws_bytes,
+                                  static_cast<cudaStream_t>(stream), 0);
+}
+
+size_t fpsg_chamfer_ws_diag_offset(int B, int N, int M) { return chamfer_diag_offset(B, N, M); }
 
 size_t fpsg_knn_workspace_bytes(int B, int C, int N, int k) { return knn_workspace(B, C, N, k); }
 

@@ -15,8 +15,6 @@
 // gradient privately in double. The sum is therefore independent of any floating-point atomic ordering (the
 // bucket order is arbitrary, but a double sum of FP32 terms is exact to far below FP32 resolution), matches the
 // oracle's double accumulation, and the gradient is written exactly once, coalesced, with no pre-zeroing.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace fpsg {
@@ -42,10 +40,11 @@ __device__ __forceinline__ float uniform_weight(float gloss, float scale, float 
     return __fdiv_rn(__fmul_rn(gloss, scale), div);
 }
 
-// seg: where the clouds and the gradient outputs live. gtotal (multi-segment loss only): device scalar, the
+// seg: where the clouds and the gradient outputs live. uniform: the upstream gradient is one value per pair, gA = gQ =
+// gloss (B,), nullptr = ones. multi (multi-segment loss, implies uniform): gtotal is a device scalar (nullptr = 1), the
 // upstream gradient of the weighted total; the pairs of segment s then receive gloss = gtotal * weight_s.
 __global__ void __launch_bounds__(kBwdThreads)
-chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, const float* __restrict__ gtotal, bool stage) {
+chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, bool multi, const float* __restrict__ gtotal, bool stage) {
     extern __shared__ __align__(16) float sQ[];  // stage: the other cloud of this pair (every gathered edge ends there)
     __shared__ int sCount[kBwdThreads];
     __shared__ int sCursor[kBwdThreads];
@@ -74,8 +73,8 @@ chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, con
     // 2*g of the two edge kinds when the upstream gradient is uniform over the pair
     float uA = 0.f, uQ = 0.f;
     if (uniform) {
-        const float glA = gtotal ? __fmul_rn(__ldg(gtotal), seg.weight[sg]) : __ldg(S.gA + b);
-        const float glQ = gtotal ? glA : __ldg(S.gQ + b);
+        const float glA = multi ? __fmul_rn(gtotal ? __ldg(gtotal) : 1.0f, seg.weight[sg]) : (S.gA ? __ldg(S.gA + b) : 1.0f);
+        const float glQ = multi ? glA : (S.gQ ? __ldg(S.gQ + b) : 1.0f);
         uA = __fmul_rn(2.0f, uniform_weight(glA, S.scaleA, S.divA));
         uQ = __fmul_rn(2.0f, uniform_weight(glQ, S.scaleQ, S.divQ));
     }
@@ -100,7 +99,9 @@ chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, con
     float ax = 0.f, ay = 0.f, az = 0.f;
     long long x = 0;
     if (live) {
-        x = S.idxA[(size_t)b * S.Na + i];
+        // clamped: an out-of-range index in a caller's idx tensor must not become an out-of-bounds read (the forward
+        // never produces one); scattered edges that point outside [0, Na) fall in no live thread's bucket below
+        x = min(max((long long)S.idxA[(size_t)b * S.Na + i], 0LL), (long long)S.Nq - 1);
         ax = __ldg(Ab + 3 * i);
         ay = __ldg(Ab + 3 * i + 1);
         az = __ldg(Ab + 3 * i + 2);
@@ -142,7 +143,7 @@ chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, con
         for (int q = 0; q < kPer; ++q)
             if (t[q] >= 0 && t[q] < kBwdThreads) atomicAdd(&sCount[(int)t[q]], 1);
         __syncthreads();
-        // exclusive scan of the 256 counts
+        // exclusive scan of the kBwdThreads counts
         const int c = sCount[tid];
         int incl = c;
 #pragma unroll
@@ -207,7 +208,7 @@ chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, con
 }
 
 int chamfer_backward_launch(const SegTable& seg, const int64_t* idx1, const int64_t* idx2, const float* g1, const float* g2,
-                            bool uniform, const float* gtotal, float w1, float w2, int B, int N, int M, cudaStream_t stream) {
+                            bool uniform, bool multi, const float* gtotal, float w1, float w2, int B, int N, int M, cudaStream_t stream) {
     if (B < 0 || N < 1 || M < 1) return fail(FPSG_EINVAL, "chamfer_bwd: need B >= 0, N >= 1, M >= 1 (got B=%d N=%d M=%d)", B, N, M);
     bool want1 = false, want2 = false;
     for (int sg = 0; sg < seg.n; ++sg) {
@@ -217,18 +218,18 @@ int chamfer_backward_launch(const SegTable& seg, const int64_t* idx1, const int6
         if (!seg.p1[sg] || !seg.p2[sg]) return fail(FPSG_EINVAL, "chamfer_bwd: null input pointer");
     }
     if (B == 0 || (!want1 && !want2)) return FPSG_OK;
-    if (!idx1 || !idx2 || (!gtotal && (!g1 || !g2))) return fail(FPSG_EINVAL, "chamfer_bwd: null input pointer");
+    if (!idx1 || !idx2 || (!uniform && (!g1 || !g2))) return fail(FPSG_EINVAL, "chamfer_bwd: null input pointer");
     if (B > 65535) return fail(FPSG_EINVAL, "chamfer_bwd: B > 65535 not supported in one call");
     BwdSide s1{true, idx1, idx2, g1, g2, w1, w2, (float)N, (float)M, N, M, want1 ? cdiv(N, kBwdThreads) : 0};
     BwdSide s2{false, idx2, idx1, g2, g1, w2, w1, (float)M, (float)N, M, N, want2 ? cdiv(M, kBwdThreads) : 0};
     const dim3 grid((unsigned)(s1.blocks + s2.blocks), (unsigned)B);
     size_t smem = align_up((size_t)(N > M ? N : M) * 12, 16);
-    static const bool no_stage = getenv("FPSG_BWD_NOSTAGE") != nullptr;  // tuning override (benchmarks only)
+    static const bool no_stage = tune_env("FPSG_BWD_NOSTAGE") != nullptr;  // tuning build only
     bool stage = smem <= kBwdStageMaxBytes && !no_stage;
     if (!stage) smem = 0;
     if (smem > 32 * 1024)  // static + dynamic beyond 48 KB needs the (per-device) opt-in
         FPSG_CUDA_OK(cudaFuncSetAttribute(chamfer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdStageMaxBytes));
-    FPSG_CUDA_OK(launch_pdl(chamfer_bwd_kernel, grid, dim3(kBwdThreads), smem, stream, seg, s1, s2, uniform, gtotal, stage));
+    FPSG_CUDA_OK(launch_pdl(chamfer_bwd_kernel, grid, dim3(kBwdThreads), smem, stream, seg, s1, s2, uniform, multi, gtotal, stage));
     return FPSG_OK;
 }
 

@@ -33,43 +33,13 @@
 //
 // Out-of-range rows and columns of ragged tiles are filled with +INF coordinates: their distances are +INF,
 // never win a strict comparison, and never equal a finite minimum.
-#include <cstdlib>
-
-#include "common.cuh"
+#include "chamfer_plan.cuh"
 
 namespace fpsg {
 
-typedef unsigned long long u64;
-
-constexpr int kSweepThreads = 128;
-constexpr int kSweepWarps = kSweepThreads / 32;
-constexpr int kUnit = 16;           // columns per scheduling unit
-constexpr int kSub = 32;            // columns per shared-memory sub-block (2 units)
-static_assert(kSub == 32, "the finalize kernel permutes a row's window with lane ^ c");
-
-
-// resident sweep CTAs per SM (register-limited): the persistent grid is this times the SM count
-constexpr int sweep_ctas_per_sm(int R, bool packed) { return packed ? 3 : (R >= 16 ? 4 : 6); }
-
-struct ChamferPlan {
-    int R;            // rows per thread in the sweep
-    bool packed;      // f32x2 arithmetic variant (R == 16 only)
-    int TN;           // rows per strip (kSweepThreads * R)
-    int strips;       // row strips per pair
-    int ups;          // 16-column units per (pair, strip)
-    long long units;  // all units of the batch (must fit an int: checked at launch)
-    int grid;         // persistent CTAs
-    int q, r;         // CTA g owns q + (g < r) units starting at g*q + min(g, r)
-    int maxslots;     // most CTAs that can intersect one (pair, strip)
-    int Mpad;         // M rounded up to a unit
-    int fin_threads;  // threads per finalize CTA
-    int nrb, ncb;     // finalize CTAs per pair: row blocks, column blocks
-    size_t rowmin_off, rowsub_off, colpart_off, losspart_off, counters_off, total_bytes;
-};
-
 static int g_sm_count = 0;
 
-static int sm_count() {
+int sm_count() {
     if (g_sm_count == 0) {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
@@ -94,7 +64,7 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
             p.R = cand[c];
         }
     }
-    if (const char* e = getenv("FPSG_SWEEP_R")) {  // tuning override (benchmarks only): 4, 8 or 16
+    if (const char* e = tune_env("FPSG_SWEEP_R")) {  // tuning build only: 4, 8 or 16
         const int v = atoi(e);
         if (v == 4 || v == 8 || v == 16) p.R = v;
     }
@@ -103,9 +73,7 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     p.ups = cdiv(M, kUnit);
     p.Mpad = p.ups * kUnit;
     p.units = (long long)B * p.strips * p.ups;
-    p.packed = false;
-    if (const char* e = getenv("FPSG_SWEEP_PACKED")) p.packed = atoi(e) != 0 && p.R == 16;  // tuning override
-    const int per_sm = sweep_ctas_per_sm(p.R, p.packed);
+    const int per_sm = sweep_ctas_per_sm(p.R);
     long long g = (long long)sm_count() * per_sm;
     // at least 4 units per CTA: every CTA that touches a (pair, strip) leaves one row partial per row for the
     // finalize kernel to merge, and small problems do not need the whole chip anyway
@@ -117,7 +85,7 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     p.maxslots = p.q > 0 ? cdiv(p.ups, p.q) + 1 : 1;
     // every finalize CTA stages a whole cloud: larger CTAs (fewer copies) once the grid exceeds a single wave anyway
     p.fin_threads = 2LL * B * (cdiv(N, 256) + cdiv(M, 256)) > 7LL * sm_count() ? 512 : 256;
-    if (const char* e = getenv("FPSG_FIN_THREADS")) {  // tuning override (benchmarks only): 256 or 512
+    if (const char* e = tune_env("FPSG_FIN_THREADS")) {  // tuning build only: 256 or 512
         const int v = atoi(e);
         if (v == 256 || v == 512) p.fin_threads = v;
     }
@@ -134,67 +102,20 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     p.losspart_off = off;
     off += align_up((size_t)B * (p.nrb + p.ncb) * sizeof(double), 256);
     p.counters_off = off;
-    off += align_up(((size_t)B + 1) * sizeof(unsigned), 256);
+    off += align_up(((size_t)B + kExtraCounters) * sizeof(unsigned), 256);
     p.total_bytes = off;
     return p;
-}
-
-struct SweepArgs {
-    SegTable seg;   // the clouds: p1 (B,N,3), p2 (B,M,3), possibly in several separately allocated segments
-    int N, M, strips, ups, q, r, maxslots, Mpad;
-    float* rowmin;  // [B*strips][maxslots][TN]   row partial minima, one slot per CTA that covered the (pair, strip) ...
-    int* rowsub;    // [B*strips][maxslots][TN]   ... and the sub-block that produced each (two arrays: the finalize kernel
-                    //                            merges the 4-byte minima and then reads one sub-block index per row)
-    u64* colpart;   // [B*strips][4 warps][Mpad]  (min bits << 32) | ballot of lanes attaining it
-    unsigned* counters;  // [B + 1] arrival counters of the finalize kernel's loss reductions; zeroed here (or nullptr)
-    int B;
-};
-
-// which CTA owns unit u under the q/r partition
-__device__ __forceinline__ int cta_of_unit(int u, int q, int r) {
-    const int cut = r * (q + 1);
-    return u < cut ? u / (q + 1) : r + (u - cut) / q;
-}
-
-// Arrival counters of the finalize kernel's reductions. The increment is an acq_rel atomic: it releases the arriving
-// thread's earlier stores (no MEMBAR.SC in front of it) and, for the last arriver, acquires everybody else's -- at the
-// place where the atomic is issued, i.e. early and off the critical path, instead of a fence in front of the final loads.
-__device__ __forceinline__ unsigned arrive_acq_rel(unsigned* counter) {
-    unsigned old;
-    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
-    return old;
-}
-
-__device__ __forceinline__ float warp_min_f32(float v) {
-    float m;
-    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
-    return m;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // sweep
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 pack2(float lo, float hi) {
-    u64 r;
-    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-// packed FP32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a): two IEEE round-to-nearest operations per issue slot,
-// bit-identical to the scalar forms
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-
-// PACKED: the distance arithmetic runs on f32x2 pairs (two rows per instruction); same bits, half the issue slots
-// for the FP32 work, at the price of duplicated column coordinates in registers (3 CTAs/SM instead of 4).
-template <int R, bool PACKED>
-__global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) chamfer_sweep_kernel(const SweepArgs a) {
+template <int R>
+__global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R)) chamfer_sweep_kernel(const SweepArgs a) {
     // Every warp keeps its own copy of the current column tile, so the warps of a CTA never wait for each other:
-    // there is no __syncthreads in this kernel. Scalar layout: AoS xyz (kSub*3 floats). Packed layout: every
-    // coordinate twice, [c] -> (x,x,y,y) and [c] -> (z,z), so a 64-bit register pair feeds both halves of an
-    // f32x2 operation. The tile is always written in full (+INF beyond the piece): a ragged tail reads +INF.
-    __shared__ __align__(16) float sCols[kSweepWarps][kSub * (PACKED ? 6 : 3)];
+    // there is no __syncthreads in this kernel. Layout: AoS xyz (kSub*3 floats). The tile is always written in full
+    // (+INF beyond the piece): a ragged tail reads +INF.
+    __shared__ __align__(16) float sCols[kSweepWarps][kSub * 3];
     __shared__ __align__(16) u64 sColRes[kSweepWarps][kSub];
     __shared__ float sPrev[R][kSweepThreads];  // best[k] as of the previous sub-block (thread-private slots)
     __shared__ int sSubIdx[R][kSweepThreads];  // sub-block that last lowered best[k]
@@ -215,23 +136,14 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
     auto piece_units = [&](int cu_, int left_) { return min(min(kUps - (cu_ % kUps), a.ups - cu_), left_); };
 
     float px[R], py[R], pz[R], best[R];
-    u64 PX[R / 2], PY[R / 2], PZ[R / 2];  // PACKED: rows paired in 64-bit registers, P[k2] = (p[2 k2], p[2 k2 + 1])
     int cur_bs = -1;                      // (pair, strip) whose rows are in registers
     int slot = 0, b = 0, strip = 0;
     float pf[kPf];    // the next piece's tile, in flight from global memory during the current piece
 
-    // where this lane's prefetched elements go in the packed tile (element e = lane + 32 q of the AoS stream)
-    int pk_off[kPf];
-#pragma unroll
-    for (int q = 0; q < kPf; ++q) {
-        const int e = lane + 32 * q, c = e / 3, comp = e - 3 * c;
-        pk_off[q] = comp < 2 ? 4 * c + 2 * comp : 4 * kSub + 2 * c;  // floats; XY block first, then Z block
-    }
-
     cudaGridDependencySynchronize();  // (PDL) the producer of p1/p2 and the previous user of the workspace are done
-    if (g == 0 && a.counters)
-        for (int q = tid; q <= a.B; q += kSweepThreads) a.counters[q] = 0u;
-    // let the finalize grid be scheduled onto SMs as this grid's CTAs retire (it waits for our completion itself)
+    if (g == 0)
+        for (int q = tid; q < a.B + kExtraCounters; q += kSweepThreads) a.counters[q] = 0u;
+    // let the next grid of the chain be scheduled onto SMs as this grid's CTAs retire (it waits for our completion itself)
     cudaTriggerProgrammaticLaunchCompletion();
 
     auto fetch = [&](int bs_, int cu_, int n_) {  // global -> registers; INF beyond the piece: padded columns never win
@@ -293,24 +205,11 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
                 sPrev[k][tid] = CUDART_INF_F;
                 sSubIdx[k][tid] = cbeg / kSub;
             }
-            if (PACKED) {
-#pragma unroll
-                for (int k = 0; k < R / 2; ++k) {
-                    PX[k] = pack2(px[2 * k], px[2 * k + 1]);
-                    PY[k] = pack2(py[2 * k], py[2 * k + 1]);
-                    PZ[k] = pack2(pz[2 * k], pz[2 * k + 1]);
-                }
-            }
         }
         // park the prefetched tile in this warp's shared-memory buffer
         __syncwarp();  // all lanes are done reading the previous tile
-        if (PACKED) {
 #pragma unroll
-            for (int q = 0; q < kPf; ++q) *reinterpret_cast<float2*>(&sCols[w][pk_off[q]]) = make_float2(pf[q], pf[q]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < kPf; ++q) sCols[w][lane + 32 * q] = pf[q];
-        }
+        for (int q = 0; q < kPf; ++q) sCols[w][lane + 32 * q] = pf[q];
 
         __syncwarp();  // tile visible to the whole warp
         if (nleft > 0) fetch(nbs, ncu, piece_units(ncu, nleft));  // overlaps the whole sub-block below
@@ -320,89 +219,40 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R, PACKED)) c
         const float* tile = sCols[w];
         u64* res = sColRes[w];
 
-        if (!PACKED) {
 #pragma unroll 1
-            for (int step = 0; step < nsteps; ++step) {
-                const float4 v0 = *reinterpret_cast<const float4*>(tile + 12 * step);      // x0 y0 z0 x1
-                const float4 v1 = *reinterpret_cast<const float4*>(tile + 12 * step + 4);  // y1 z1 x2 y2
-                const float4 v2 = *reinterpret_cast<const float4*>(tile + 12 * step + 8);  // z2 x3 y3 z3
-                float c0m = CUDART_INF_F, c1m = CUDART_INF_F, c2m = CUDART_INF_F, c3m = CUDART_INF_F;
+        for (int step = 0; step < nsteps; ++step) {
+            const float4 v0 = *reinterpret_cast<const float4*>(tile + 12 * step);      // x0 y0 z0 x1
+            const float4 v1 = *reinterpret_cast<const float4*>(tile + 12 * step + 4);  // y1 z1 x2 y2
+            const float4 v2 = *reinterpret_cast<const float4*>(tile + 12 * step + 8);  // z2 x3 y3 z3
+            float c0m = CUDART_INF_F, c1m = CUDART_INF_F, c2m = CUDART_INF_F, c3m = CUDART_INF_F;
 #pragma unroll
-                for (int k = 0; k < R; k += 2) {
-                    const float a0 = sqdist(px[k], py[k], pz[k], v0.x, v0.y, v0.z);
-                    const float a1 = sqdist(px[k], py[k], pz[k], v0.w, v1.x, v1.y);
-                    const float a2 = sqdist(px[k], py[k], pz[k], v1.z, v1.w, v2.x);
-                    const float a3 = sqdist(px[k], py[k], pz[k], v2.y, v2.z, v2.w);
-                    const float b0 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v0.x, v0.y, v0.z);
-                    const float b1 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v0.w, v1.x, v1.y);
-                    const float b2 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v1.z, v1.w, v2.x);
-                    const float b3 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v2.y, v2.z, v2.w);
-                    best[k] = min3(min3(best[k], a0, a1), a2, a3);
-                    best[k + 1] = min3(min3(best[k + 1], b0, b1), b2, b3);
-                    c0m = min3(c0m, a0, b0);
-                    c1m = min3(c1m, a1, b1);
-                    c2m = min3(c2m, a2, b2);
-                    c3m = min3(c3m, a3, b3);
-                }
-                // column direction: warp minimum + the lanes that attain it, one 8-byte record per column
-                const float m0 = warp_min_f32(c0m), m1 = warp_min_f32(c1m), m2 = warp_min_f32(c2m), m3 = warp_min_f32(c3m);
-                const unsigned h0 = __ballot_sync(0xffffffffu, c0m == m0);
-                const unsigned h1 = __ballot_sync(0xffffffffu, c1m == m1);
-                const unsigned h2 = __ballot_sync(0xffffffffu, c2m == m2);
-                const unsigned h3 = __ballot_sync(0xffffffffu, c3m == m3);
-                if (lane == 0) {
-                    res[4 * step + 0] = ((u64)__float_as_uint(m0) << 32) | h0;
-                    res[4 * step + 1] = ((u64)__float_as_uint(m1) << 32) | h1;
-                    res[4 * step + 2] = ((u64)__float_as_uint(m2) << 32) | h2;
-                    res[4 * step + 3] = ((u64)__float_as_uint(m3) << 32) | h3;
-                }
+            for (int k = 0; k < R; k += 2) {
+                const float a0 = sqdist(px[k], py[k], pz[k], v0.x, v0.y, v0.z);
+                const float a1 = sqdist(px[k], py[k], pz[k], v0.w, v1.x, v1.y);
+                const float a2 = sqdist(px[k], py[k], pz[k], v1.z, v1.w, v2.x);
+                const float a3 = sqdist(px[k], py[k], pz[k], v2.y, v2.z, v2.w);
+                const float b0 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v0.x, v0.y, v0.z);
+                const float b1 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v0.w, v1.x, v1.y);
+                const float b2 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v1.z, v1.w, v2.x);
+                const float b3 = sqdist(px[k + 1], py[k + 1], pz[k + 1], v2.y, v2.z, v2.w);
+                best[k] = min3(min3(best[k], a0, a1), a2, a3);
+                best[k + 1] = min3(min3(best[k + 1], b0, b1), b2, b3);
+                c0m = min3(c0m, a0, b0);
+                c1m = min3(c1m, a1, b1);
+                c2m = min3(c2m, a2, b2);
+                c3m = min3(c3m, a3, b3);
             }
-        } else {
-            const ulonglong2* txy = reinterpret_cast<const ulonglong2*>(tile);           // [c] = ((x,x), (y,y))
-            const ulonglong2* tz = reinterpret_cast<const ulonglong2*>(tile + 4 * kSub);  // [c/2] = ((z,z), (z',z'))
-#pragma unroll 1
-            for (int step = 0; step < nsteps; ++step) {
-                u64 QX[4], QY[4], QZ[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const ulonglong2 xy = txy[4 * step + c];
-                    QX[c] = xy.x;
-                    QY[c] = xy.y;
-                }
-                {
-                    const ulonglong2 z01 = tz[2 * step], z23 = tz[2 * step + 1];
-                    QZ[0] = z01.x;
-                    QZ[1] = z01.y;
-                    QZ[2] = z23.x;
-                    QZ[3] = z23.y;
-                }
-                float cm[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
-#pragma unroll
-                for (int k = 0; k < R / 2; ++k) {
-                    float lo[4], hi[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const u64 dx = sub2(QX[c], PX[k]), dy = sub2(QY[c], PY[k]), dz = sub2(QZ[c], PZ[k]);
-                        u64 t = mul2(dy, dy);
-                        t = fma2(dx, dx, t);
-                        t = fma2(dz, dz, t);
-                        unpack2(t, lo[c], hi[c]);
-                        cm[c] = min3(cm[c], lo[c], hi[c]);
-                    }
-                    best[2 * k] = min3(min3(best[2 * k], lo[0], lo[1]), lo[2], lo[3]);
-                    best[2 * k + 1] = min3(min3(best[2 * k + 1], hi[0], hi[1]), hi[2], hi[3]);
-                }
-                const float m0 = warp_min_f32(cm[0]), m1 = warp_min_f32(cm[1]), m2 = warp_min_f32(cm[2]), m3 = warp_min_f32(cm[3]);
-                const unsigned h0 = __ballot_sync(0xffffffffu, cm[0] == m0);
-                const unsigned h1 = __ballot_sync(0xffffffffu, cm[1] == m1);
-                const unsigned h2 = __ballot_sync(0xffffffffu, cm[2] == m2);
-                const unsigned h3 = __ballot_sync(0xffffffffu, cm[3] == m3);
-                if (lane == 0) {
-                    res[4 * step + 0] = ((u64)__float_as_uint(m0) << 32) | h0;
-                    res[4 * step + 1] = ((u64)__float_as_uint(m1) << 32) | h1;
-                    res[4 * step + 2] = ((u64)__float_as_uint(m2) << 32) | h2;
-                    res[4 * step + 3] = ((u64)__float_as_uint(m3) << 32) | h3;
-                }
+            // column direction: warp minimum + the lanes that attain it, one 8-byte record per column
+            const float m0 = warp_min_f32(c0m), m1 = warp_min_f32(c1m), m2 = warp_min_f32(c2m), m3 = warp_min_f32(c3m);
+            const unsigned h0 = __ballot_sync(0xffffffffu, c0m == m0);
+            const unsigned h1 = __ballot_sync(0xffffffffu, c1m == m1);
+            const unsigned h2 = __ballot_sync(0xffffffffu, c2m == m2);
+            const unsigned h3 = __ballot_sync(0xffffffffu, c3m == m3);
+            if (lane == 0) {
+                res[4 * step + 0] = ((u64)__float_as_uint(m0) << 32) | h0;
+                res[4 * step + 1] = ((u64)__float_as_uint(m1) << 32) | h1;
+                res[4 * step + 2] = ((u64)__float_as_uint(m2) << 32) | h2;
+                res[4 * step + 3] = ((u64)__float_as_uint(m3) << 32) | h3;
             }
         }
 
@@ -539,36 +389,10 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
         int sub = 0;
         if (valid) {
             const int strip = i / TN, within = i - strip * TN;
-            const int bs = b * a.strips + strip;
-            const int u0 = bs * a.ups;
-            const int g0 = cta_of_unit(u0, a.q, a.r), g1 = cta_of_unit(u0 + a.ups - 1, a.q, a.r);
-            // Slots are in ascending column order, so the first slot (strict '<') that attains the minimum holds the
-            // lowest sub-block among equal minima: the reference's strict-'<' ascending scan at sub-block granularity.
-            // All 4-byte minima of a batch are in flight together (one L2 round trip; slots past the last one re-read
-            // it), then one dependent load fetches the winner's sub-block index.
-            const size_t ro = (size_t)bs * a.maxslots * TN + within;
-            const float* rm = a.rowmin + ro;
-            const int nsl = g1 - g0 + 1;
-            int ms = 0;
-            constexpr int kSlotBatch = 24;
-            for (int s0 = 0; s0 < nsl; s0 += kSlotBatch) {
-                float v[kSlotBatch];
-#pragma unroll
-                for (int s = 0; s < kSlotBatch; ++s) v[s] = __ldcg(rm + (unsigned)(min(s0 + s, nsl - 1) * TN));  // < maxslots * TN: 32 bits
-                if (s0 == 0) {
-                    ax = __ldg(p1b + 3 * i);
-                    ay = __ldg(p1b + 3 * i + 1);
-                    az = __ldg(p1b + 3 * i + 2);
-                }
-#pragma unroll
-                for (int s = 0; s < kSlotBatch; ++s) {
-                    if (v[s] < m) {
-                        m = v[s];
-                        ms = min(s0 + s, nsl - 1);
-                    }
-                }
-            }
-            sub = __ldcg(a.rowsub + ro + (unsigned)(ms * TN));
+            ax = __ldg(p1b + 3 * i);
+            ay = __ldg(p1b + 3 * i + 1);
+            az = __ldg(p1b + 3 * i + 2);
+            merge_row_partials(a.rowmin, a.rowsub, b * a.strips + strip, within, TN, a.ups, a.q, a.r, a.maxslots, m, sub);
             mine = m;
         }
         stage_cloud();
@@ -597,7 +421,10 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             if (valid) {
                 if (a.dist1) out_dist = a.dist1 + (size_t)b * a.N + i;
                 out_idx = a.idx1 + (size_t)b * a.N + i;
-                out_val = f == 0x7fffffff ? sub * kSub : sub * kSub + f;
+                // no candidate equals the merged minimum: cannot happen for finite minima (counted, tests assert zero);
+                // a row without any finite distance (NaN / Inf coordinates) keeps index 0 like a strict-'<' scan from +INF
+                if (f == 0x7fffffff && m != CUDART_INF_F) atomicAdd(a.counters + a.B + 1, 1u);
+                out_val = (f == 0x7fffffff || m == CUDART_INF_F) ? (m == CUDART_INF_F ? 0 : sub * kSub) : sub * kSub + f;
             }
         } else {
         constexpr int kBatch = 8;  // rows whose candidate loads are put in flight together (the loop is latency-bound)
@@ -618,8 +445,8 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             for (int r = 0; r < kBatch; ++r) {
                 const float4 pt = sPt[w * 32 + rb + r];
                 const int j0 = sBase[w * 32 + rb + r];
-                int f = j0;
-                bool done = false;
+                int f = pt.w == CUDART_INF_F ? 0 : -1 - j0;  // negative: nothing matched yet
+                bool done = pt.w == CUDART_INF_F;
 #pragma unroll
                 for (int h = 0; h < kH; ++h) {
                     const float d = sqdist(pt.x, pt.y, pt.z, cx[r][h], cy[r][h], cz[r][h]);
@@ -638,6 +465,10 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             if (a.dist1) out_dist = a.dist1 + (size_t)b * a.N + i;
             out_idx = a.idx1 + (size_t)b * a.N + i;
             out_val = sFound[tid];
+            if (out_val < 0) {
+                atomicAdd(a.counters + a.B + 1, 1u);
+                out_val = -1 - out_val;
+            }
         }
     } else {
         // ---- columns: each thread merges strips x warps ... ----
@@ -646,20 +477,10 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
         float m = CUDART_INF_F, qx = 0.f, qy = 0.f, qz = 0.f;
         int r0 = 0;
         if (valid) {
-            for (int s = 0; s < a.strips; ++s) {
-#pragma unroll
-                for (int ww = 0; ww < kSweepWarps; ++ww) {  // ascending (strip, warp) = ascending rows
-                    const u64 rec = a.colpart[(((size_t)b * a.strips + s) * kSweepWarps + ww) * a.Mpad + j];
-                    const float v = __uint_as_float((unsigned)(rec >> 32));
-                    if (v < m) {
-                        m = v;
-                        r0 = (s * kSweepThreads + ww * 32 + ((unsigned)rec ? __ffs((unsigned)rec) - 1 : 0)) * a.R;
-                    }
-                }
-            }
             qx = __ldg(p2b + 3 * j);
             qy = __ldg(p2b + 3 * j + 1);
             qz = __ldg(p2b + 3 * j + 2);
+            merge_col_partials(a.colpart, b, j, a.strips, a.Mpad, a.R, m, r0);
             mine = m;
         }
         stage_cloud();
@@ -685,7 +506,8 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             if (valid) {
                 if (a.dist2) out_dist = a.dist2 + (size_t)b * a.M + j;
                 out_idx = a.idx2 + (size_t)b * a.M + j;
-                out_val = f == 0x7fffffff ? min(r0, last) : r0 + f;
+                if (f == 0x7fffffff && m != CUDART_INF_F) atomicAdd(a.counters + a.B + 1, 1u);
+                out_val = m == CUDART_INF_F ? 0 : (f == 0x7fffffff ? min(r0, last) : r0 + f);
             }
         } else {
         constexpr int kCB = 4;  // iterations whose candidate loads are in flight together (R is a multiple of 4)
@@ -706,7 +528,8 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
                 const int rr0 = sBase[c];
                 const float d = sqdist(pt.x, pt.y, pt.z, rx[t], ry[t], rz[t]);
                 const unsigned hit = __ballot_sync(0xffffffffu, d == pt.w) & gmask;
-                if (off == 0) sFound[c] = hit ? min(rr0 + (__ffs(hit) - 1 - grp * R), last) : min(rr0, last);
+                if (off == 0)
+                    sFound[c] = pt.w == CUDART_INF_F ? 0 : (hit ? min(rr0 + (__ffs(hit) - 1 - grp * R), last) : -1 - min(rr0, last));
             }
         }
         }
@@ -715,6 +538,10 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             if (a.dist2) out_dist = a.dist2 + (size_t)b * a.M + j;
             out_idx = a.idx2 + (size_t)b * a.M + j;
             out_val = sFound[tid];
+            if (out_val < 0) {
+                atomicAdd(a.counters + a.B + 1, 1u);
+                out_val = -1 - out_val;
+            }
         }
     }
 
@@ -768,17 +595,12 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-// sweep_only: launch just the sweep kernel (partials land in the workspace); bench.py times the dominant kernel
-// alone this way for the roofline line.
-int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
-                           int64_t* idx2, float* loss, float* totals, float w1, float w2, void* ws, size_t ws_bytes,
-                           cudaStream_t stream, bool sweep_only) {
+// Validation + plan + workspace carving shared by every Chamfer forward entry point.
+int chamfer_prepare(const SegTable& seg, int B, int N, int M, void* ws, size_t ws_bytes, ChamferPlan* out) {
     if (B < 0 || N < 1 || M < 1) return fail(FPSG_EINVAL, "chamfer: need B >= 0, N >= 1, M >= 1 (got B=%d N=%d M=%d)", B, N, M);
     if (B == 0) return FPSG_OK;
     for (int sg = 0; sg < seg.n; ++sg)
         if (seg.b0[sg + 1] > seg.b0[sg] && (!seg.p1[sg] || !seg.p2[sg])) return fail(FPSG_EINVAL, "chamfer: null p1/p2");
-    if (!sweep_only && (!idx1 || !idx2)) return fail(FPSG_EINVAL, "chamfer: null idx1/idx2");
-    if (totals && !loss) return fail(FPSG_EINVAL, "chamfer: totals need the per-pair loss buffer");
     if (B > 65535) return fail(FPSG_EINVAL, "chamfer: B > 65535 not supported in one call");
     if ((long long)N * 3 > 0x7fffffffLL || (long long)M * 3 > 0x7fffffffLL) return fail(FPSG_EINVAL, "chamfer: cloud too large");
     const ChamferPlan pl = make_chamfer_plan(B, N, M);
@@ -786,30 +608,36 @@ int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist
     if (!ws || ws_bytes < pl.total_bytes)
         return fail(FPSG_EWORKSPACE, "chamfer: workspace of %zu bytes required, %zu given", pl.total_bytes, ws ? ws_bytes : (size_t)0);
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(FPSG_EWORKSPACE, "chamfer: workspace must be 256-byte aligned");
-    char* base = static_cast<char*>(ws);
-    float* rowmin = reinterpret_cast<float*>(base + pl.rowmin_off);
-    int* rowsub = reinterpret_cast<int*>(base + pl.rowsub_off);
-    u64* colpart = reinterpret_cast<u64*>(base + pl.colpart_off);
-    double* losspart = loss ? reinterpret_cast<double*>(base + pl.losspart_off) : nullptr;
-    unsigned* counters = loss ? reinterpret_cast<unsigned*>(base + pl.counters_off) : nullptr;
+    *out = pl;
+    return FPSG_OK;
+}
 
-    const SweepArgs sa{seg, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowmin, rowsub, colpart, counters, B};
+int chamfer_sweep_launch(const SegTable& seg, const ChamferPlan& pl, int B, int N, int M, void* ws, cudaStream_t stream) {
+    char* base = static_cast<char*>(ws);
+    const SweepArgs sa{seg, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, reinterpret_cast<float*>(base + pl.rowmin_off),
+                       reinterpret_cast<int*>(base + pl.rowsub_off), reinterpret_cast<u64*>(base + pl.colpart_off),
+                       reinterpret_cast<unsigned*>(base + pl.counters_off), B};
     const dim3 sgrid((unsigned)pl.grid), sblock(kSweepThreads);
-    if (pl.R == 16 && pl.packed)
-        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<16, true>, sgrid, sblock, 0, stream, sa));
-    else if (pl.R == 16)
-        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<16, false>, sgrid, sblock, 0, stream, sa));
+    if (pl.R == 16)
+        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<16>, sgrid, sblock, 0, stream, sa));
     else if (pl.R == 8)
-        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<8, false>, sgrid, sblock, 0, stream, sa));
+        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<8>, sgrid, sblock, 0, stream, sa));
     else
-        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<4, false>, sgrid, sblock, 0, stream, sa));
-    if (sweep_only) return FPSG_OK;
-    FinalizeArgs fa{seg, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, rowmin, rowsub, colpart,
-                          dist1, dist2, idx1, idx2, losspart, counters, loss, w1, w2, pl.nrb, pl.ncb, totals, B, 0};
+        FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<4>, sgrid, sblock, 0, stream, sa));
+    return FPSG_OK;
+}
+
+int chamfer_finalize_launch(const SegTable& seg, const ChamferPlan& pl, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
+                            int64_t* idx2, float* loss, float* totals, float w1, float w2, void* ws, cudaStream_t stream) {
+    char* base = static_cast<char*>(ws);
+    double* losspart = loss ? reinterpret_cast<double*>(base + pl.losspart_off) : nullptr;
+    FinalizeArgs fa{seg, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, reinterpret_cast<const float*>(base + pl.rowmin_off),
+                    reinterpret_cast<const int*>(base + pl.rowsub_off), reinterpret_cast<const u64*>(base + pl.colpart_off),
+                    dist1, dist2, idx1, idx2, losspart, reinterpret_cast<unsigned*>(base + pl.counters_off), loss, w1, w2, pl.nrb, pl.ncb, totals, B, 0};
     if (pl.nrb + pl.ncb > 65535) return fail(FPSG_EINVAL, "chamfer: N + M too large for one call");
     const dim3 fgrid((unsigned)B, (unsigned)(pl.nrb + pl.ncb));
     size_t fin_smem = align_up((size_t)(N > M ? N : M), 32) * 12;  // whole 32-point windows
-    static const bool no_stage = getenv("FPSG_FIN_NOSTAGE") != nullptr;  // tuning override (benchmarks only)
+    static const bool no_stage = tune_env("FPSG_FIN_NOSTAGE") != nullptr;  // tuning build only
     if (fin_smem <= kFinStageMaxBytes && !no_stage) {
         // more than 48 KB of shared memory per CTA (static + dynamic) needs an opt-in; it is per device, so it is repeated
         // per launch (as the kNN launches do) -- the c1 shapes (24 KB) never get here
@@ -829,6 +657,28 @@ int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist
         FPSG_CUDA_OK(launch_pdl(chamfer_finalize_kernel<256>, fgrid, dim3(256), fin_smem, stream, fa));
     FPSG_CUDA_OK(cudaGetLastError());
     return FPSG_OK;
+}
+
+// sweep_only: launch just the sweep kernel (partials land in the workspace); bench.py times the dominant kernel
+// alone this way for the roofline line.
+int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
+                           int64_t* idx2, float* loss, float* totals, float w1, float w2, void* ws, size_t ws_bytes,
+                           cudaStream_t stream, bool sweep_only) {
+    if (!sweep_only && B > 0 && (!idx1 || !idx2)) return fail(FPSG_EINVAL, "chamfer: null idx1/idx2");
+    if (totals && !loss) return fail(FPSG_EINVAL, "chamfer: totals need the per-pair loss buffer");
+    ChamferPlan pl;
+    const int rc = chamfer_prepare(seg, B, N, M, ws, ws_bytes, &pl);
+    if (rc != FPSG_OK || B == 0) return rc;
+    const int rs = chamfer_sweep_launch(seg, pl, B, N, M, ws, stream);
+    if (rs != FPSG_OK || sweep_only) return rs;
+    return chamfer_finalize_launch(seg, pl, B, N, M, dist1, dist2, idx1, idx2, loss, totals, w1, w2, ws, stream);
+}
+
+// Offset of the diagnostic counter (arg-min recoveries that found no candidate equal to the merged minimum) in a
+// workspace of this shape; zeroed by every forward, must read 0 after it.
+size_t chamfer_diag_offset(int B, int N, int M) {
+    if (B <= 0 || N < 1 || M < 1) return 0;
+    return make_chamfer_plan(B, N, M).counters_off + ((size_t)B + 1) * sizeof(unsigned);
 }
 
 size_t chamfer_forward_workspace(int B, int N, int M) {

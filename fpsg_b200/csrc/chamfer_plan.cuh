@@ -1,0 +1,124 @@
+// Work decomposition and workspace layout shared by the Chamfer kernels (chamfer_fwd.cu: sweep + finalize,
+// chamfer_finish.cu: fused finalize + backward).
+#pragma once
+#include "common.cuh"
+
+namespace fpsg {
+
+typedef unsigned long long u64;
+
+constexpr int kSweepThreads = 128;
+constexpr int kSweepWarps = kSweepThreads / 32;
+constexpr int kUnit = 16;  // columns per scheduling unit
+constexpr int kSub = 32;   // columns per shared-memory sub-block (2 units)
+static_assert(kSub == 32, "the arg-min recovery permutes a row's window with lane ^ c");
+
+// resident sweep CTAs per SM (register-limited): the persistent grid is this times the SM count
+constexpr int sweep_ctas_per_sm(int R) { return R >= 16 ? 4 : 6; }
+
+struct ChamferPlan {
+    int R;            // rows per thread in the sweep
+    int TN;           // rows per strip (kSweepThreads * R)
+    int strips;       // row strips per pair
+    int ups;          // 16-column units per (pair, strip)
+    long long units;  // all units of the batch (must fit an int: checked at launch)
+    int grid;         // persistent CTAs
+    int q, r;         // CTA g owns q + (g < r) units starting at g*q + min(g, r)
+    int maxslots;     // most CTAs that can intersect one (pair, strip)
+    int Mpad;         // M rounded up to a unit
+    int fin_threads;  // threads per finalize CTA
+    int nrb, ncb;     // finalize CTAs per pair: row blocks, column blocks
+    size_t rowmin_off, rowsub_off, colpart_off, losspart_off, counters_off, total_bytes;
+};
+
+// counters region of the workspace: [0, B) per-pair arrival counters, [B] batch-level arrival counter,
+// [B + 1] diagnostic: arg-min recoveries that found no candidate equal to the merged minimum (must stay 0)
+constexpr int kExtraCounters = 2;
+
+ChamferPlan make_chamfer_plan(int B, int N, int M);
+int sm_count();
+
+struct SweepArgs {
+    SegTable seg;   // the clouds: p1 (B,N,3), p2 (B,M,3), possibly in several separately allocated segments
+    int N, M, strips, ups, q, r, maxslots, Mpad;
+    float* rowmin;  // [B*strips][maxslots][TN]   row partial minima, one slot per CTA that covered the (pair, strip) ...
+    int* rowsub;    // [B*strips][maxslots][TN]   ... and the sub-block that produced each (two arrays: the merge reads the
+                    //                            4-byte minima and then one sub-block index per row)
+    u64* colpart;   // [B*strips][4 warps][Mpad]  (min bits << 32) | ballot of lanes attaining it
+    unsigned* counters;  // [B + kExtraCounters], zeroed by the sweep kernel
+    int B;
+};
+
+#ifdef __CUDACC__
+// which CTA owns unit u under the q/r partition
+__device__ __forceinline__ int cta_of_unit(int u, int q, int r) {
+    const int cut = r * (q + 1);
+    return u < cut ? u / (q + 1) : r + (u - cut) / q;
+}
+
+// Arrival counters of the loss reductions. The increment is an acq_rel atomic: it releases the arriving thread's
+// earlier stores (no MEMBAR.SC in front of it) and, for the last arriver, acquires everybody else's -- at the place
+// where the atomic is issued, i.e. early and off the critical path, instead of a fence in front of the final loads.
+__device__ __forceinline__ unsigned arrive_acq_rel(unsigned* counter) {
+    unsigned old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    return old;
+}
+
+__device__ __forceinline__ float warp_min_f32(float v) {
+    float m;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+    return m;
+}
+
+// Row merge shared by the finalize and the finish kernels: minimum over the slots of the CTAs that covered the
+// row's (pair, strip), in ascending slot (= column) order under strict '<', and the sub-block that produced it.
+// Slots are in ascending column order, so the first slot that attains the minimum holds the lowest sub-block among
+// equal minima: the reference's strict-'<' ascending scan at sub-block granularity. All 4-byte minima of a batch
+// are in flight together (one L2 round trip; slots past the last one re-read it), then one dependent load fetches
+// the winner's sub-block index.
+__device__ __forceinline__ void merge_row_partials(const float* __restrict__ rowmin, const int* __restrict__ rowsub, int bs, int within,
+                                                   int TN, int ups, int q, int r, int maxslots, float& m, int& sub) {
+    const int u0 = bs * ups;
+    const int g0 = cta_of_unit(u0, q, r), g1 = cta_of_unit(u0 + ups - 1, q, r);
+    const size_t ro = (size_t)bs * maxslots * TN + within;
+    const float* rm = rowmin + ro;
+    const int nsl = g1 - g0 + 1;
+    int ms = 0;
+    m = CUDART_INF_F;
+    constexpr int kSlotBatch = 24;
+    for (int s0 = 0; s0 < nsl; s0 += kSlotBatch) {
+        float v[kSlotBatch];
+#pragma unroll
+        for (int s = 0; s < kSlotBatch; ++s) v[s] = __ldcg(rm + (unsigned)(min(s0 + s, nsl - 1) * TN));  // < maxslots * TN: 32 bits
+#pragma unroll
+        for (int s = 0; s < kSlotBatch; ++s) {
+            if (v[s] < m) {
+                m = v[s];
+                ms = min(s0 + s, nsl - 1);
+            }
+        }
+    }
+    sub = __ldcg(rowsub + ro + (unsigned)(ms * TN));
+}
+
+// Column merge: minimum over strips x warps in ascending (strip, warp) = ascending row order; r0 = first row of the
+// winning thread's R consecutive rows.
+__device__ __forceinline__ void merge_col_partials(const u64* __restrict__ colpart, int b, int j, int strips, int Mpad, int R, float& m, int& r0) {
+    m = CUDART_INF_F;
+    r0 = 0;
+    for (int s = 0; s < strips; ++s) {
+#pragma unroll
+        for (int ww = 0; ww < kSweepWarps; ++ww) {
+            const u64 rec = __ldcg(colpart + (((size_t)b * strips + s) * kSweepWarps + ww) * Mpad + j);
+            const float v = __uint_as_float((unsigned)(rec >> 32));
+            if (v < m) {
+                m = v;
+                r0 = (s * kSweepThreads + ww * 32 + ((unsigned)rec ? __ffs((unsigned)rec) - 1 : 0)) * R;
+            }
+        }
+    }
+}
+#endif
+
+}  // namespace fpsg

@@ -4,6 +4,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <utility>
 
 #include "../../include/fpsg_b200.h"
@@ -20,6 +21,15 @@ int fail(int code, const char* fmt, ...);
             return ::fpsg::fail(FPSG_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
                                 __FILE__, __LINE__);                                                  \
     } while (0)
+
+// Tuning switches (FPSG_* environment variables used by the ablations under bench_micro/) exist only in builds made
+// with -DFPSG_TUNING (FPSG_BUILD_TUNING=1 python fpsg_b200/build.py). The product build compiles them out: no launch
+// path reads the environment.
+#ifdef FPSG_TUNING
+inline const char* tune_env(const char* name) { return std::getenv(name); }
+#else
+inline const char* tune_env(const char*) { return nullptr; }
+#endif
 
 constexpr size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }

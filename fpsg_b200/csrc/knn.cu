@@ -13,8 +13,6 @@
 //   pd   = rn( rn(-xx_j + 2*dot) - xx_i )               (model.py:16; -2*dot is exact, so the first
 //                                                        subtraction is one rounding = fma(2, dot, -xx_j))
 // Ranking: larger pd first; equal pd ordered by ascending index (torch.topk leaves ties unspecified).
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace fpsg {
@@ -1180,7 +1178,7 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
     p.npad = 0;
     p.chunk = 0;
     p.nbuf = 1;
-    if (p.KR == 1 && C != 3 && !getenv("FPSG_KNN_INSERT") && !getenv("FPSG_KNN_NOGEMM")) {
+    if (p.KR == 1 && C != 3 && !tune_env("FPSG_KNN_INSERT") && !tune_env("FPSG_KNN_NOGEMM")) {
         long long jg = (long long)(kKnnTileBytes / sizeof(float)) / (C + 1) / 128 * 128;
         if (jg < 128) jg = 128;
         const long long npad128 = (N + 127) / 128 * 128;
@@ -1199,7 +1197,7 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
             if (chunk < 1) chunk = 1;
             if (chunk > (size_t)B) chunk = (size_t)B;
             const size_t row_bytes = chunk * cloud_bytes;
-            if (N <= kRowsMaxN && !getenv("FPSG_KNN_NOROWS")) {
+            if (N <= kRowsMaxN && !tune_env("FPSG_KNN_NOROWS")) {
                 p.rows = true;
                 p.npad = (int)npad;
                 p.chunk = (int)chunk;
@@ -1211,10 +1209,12 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
             return p;
         }
     }
-    if (p.KR == 1 && !getenv("FPSG_KNN_INSERT"))  // bulk top-k kernel: tile + (generic C) query values + candidate buffers
+    if (p.KR == 1 && !tune_env("FPSG_KNN_INSERT"))  // bulk top-k kernel: tile + (generic C) query values + candidate buffers
         p.smem = ((size_t)C * p.J + p.J + (C == 3 ? 0 : (size_t)kKnnWarps * C * kKnnQB)) * sizeof(float) + (size_t)kKnnWarps * kKnnQB * 64 * sizeof(u64);
     else if (C == 3)
         p.smem = ((size_t)C * p.J + p.J) * sizeof(float) + (size_t)kKnnRows * 32 * p.KR * (sizeof(float) + sizeof(int));
+    else if (p.KR == 4)  // generic C, 64 < k <= 128: knn_kernel<4,false> (tile + norms + one query row per warp + the lists)
+        p.smem = ((size_t)C * p.J + p.J + (size_t)kKnnWarps * C) * sizeof(float) + (size_t)kKnnRows * 32 * p.KR * (sizeof(float) + sizeof(int));
     else
         p.smem = ((size_t)C * p.J + p.J + (size_t)kKnnWarps * C * kKnnQB) * sizeof(float);
     p.ws_bytes = align_up((size_t)B * N * sizeof(float), 256);
@@ -1293,8 +1293,9 @@ int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx,
     if (B > 65535) return fail(FPSG_EINVAL, "knn: B > 65535 not supported in one call");
     if ((size_t)C * 32 * sizeof(float) > 160 * 1024) return fail(FPSG_EINVAL, "knn: C=%d too large", C);
     const KnnPlan p = make_knn_plan(B, C, N, k);
+    if (p.smem > 227 * 1024) return fail(FPSG_EINVAL, "knn: C=%d with k=%d needs %zu bytes of shared memory per CTA (limit 227 KB)", C, k, p.smem);
     if (!ws || ws_bytes < p.ws_bytes) return fail(FPSG_EWORKSPACE, "knn: workspace of %zu bytes required, %zu given", p.ws_bytes, ws ? ws_bytes : (size_t)0);
-    if (C == 3 && k <= 32 && N <= kSelMaxN && !getenv("FPSG_KNN_BULK")) {  // threshold-selection kernel (needs no workspace)
+    if (C == 3 && k <= 32 && N <= kSelMaxN && !tune_env("FPSG_KNN_BULK")) {  // threshold-selection kernel (needs no workspace)
         const KnnSelPlan sp = knn_select_plan(N);
         if (sp.smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
         knn_select_kernel<<<dim3((unsigned)cdiv(N, kSelQ), (unsigned)B), kSelThreads, sp.smem, stream>>>(x, N, k, sp.nfine, sp.fsh, idx);
@@ -1307,7 +1308,7 @@ int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx,
     const bool c3 = (C == 3);
     switch (p.KR) {
         case 1:
-            if (getenv("FPSG_KNN_INSERT"))  // tuning override: the shuffle-insertion kernels also serve k <= 32
+            if (tune_env("FPSG_KNN_INSERT"))  // tuning override: the shuffle-insertion kernels also serve k <= 32
                 return c3 ? knn_launch_t<1, true>(x, xx, B, C, N, k, p, idx, stream) : knn_launch_blocked<1>(x, xx, B, C, N, k, p, idx, stream);
             if (p.rows)
                 return knn_launch_rows(x, xx, reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)B * N * sizeof(float), 256)), B, C, N, k,

@@ -73,7 +73,7 @@ int fpsg_chamfer_bwd(const float* p1, const float* p2, const int64_t* idx1, cons
 int fpsg_chamfer_loss_fwd(const float* p1, const float* p2, int B, int N, int M, float w1, float w2, float* loss,
                           float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, void* ws, size_t ws_bytes,
                           fpsg_stream_t stream);
-/* gloss (B,): upstream gradient of loss; equivalent to fpsg_chamfer_bwd with g1 = gloss*w1/N, g2 = gloss*w2/M. */
+/* gloss (B,): upstream gradient of loss (required); equivalent to fpsg_chamfer_bwd with g1 = gloss*w1/N, g2 = gloss*w2/M. */
 int fpsg_chamfer_loss_bwd(const float* p1, const float* p2, const int64_t* idx1, const int64_t* idx2,
                           const float* gloss, float w1, float w2, int B, int N, int M, float* gp1, float* gp2,
                           void* ws, size_t ws_bytes, fpsg_stream_t stream);
@@ -103,6 +103,36 @@ int fpsg_chamfer_multi_loss_fwd(const fpsg_chamfer_segment_t* segs_host, int nse
 int fpsg_chamfer_multi_loss_bwd(const fpsg_chamfer_segment_t* segs_host, int nseg, const int64_t* idx1,
                                 const int64_t* idx2, const float* gtotal, float w1, float w2, int N, int M,
                                 fpsg_stream_t stream);
+
+/* Loss forward AND backward in one call, for a loss whose upstream gradient is known when the step is launched --
+ * the reference's training step: `loss = pc_metric(syn, ref).sum()` (src/models/few_shot.py:110,117), weighted total
+ * (:121), `ttl_loss.backward()` (src/trainNetwork.py:144): the gradient that reaches `loss` is a constant.
+ * gloss (B,) DEVICE, the upstream gradient of loss, or NULL = ones (the `.sum()` case). Outputs as
+ * fpsg_chamfer_loss_fwd (dist1/dist2 optional, idx1/idx2 required) plus gp1 (B,N,3) / gp2 (B,M,3), each optional.
+ * Results are identical to fpsg_chamfer_loss_fwd followed by fpsg_chamfer_loss_bwd; for clouds of up to 4096 points
+ * the merge, the arg-min recovery, the loss and the backward of a pair run in ONE kernel (a thread-block cluster per
+ * pair, inverted index through distributed shared memory), larger clouds take the three-kernel chain.
+ * Workspace: fpsg_chamfer_fwd_workspace_bytes(B, N, M). */
+int fpsg_chamfer_loss_fwd_bwd(const float* p1, const float* p2, int B, int N, int M, float w1, float w2,
+                              const float* gloss, float* loss, float* dist1, float* dist2, int64_t* idx1,
+                              int64_t* idx2, float* gp1, float* gp2, void* ws, size_t ws_bytes, fpsg_stream_t stream);
+/* The multi-segment form: fpsg_chamfer_multi_loss_fwd + fpsg_chamfer_multi_loss_bwd in one call. gtotal: DEVICE
+ * scalar, the upstream gradient of totals[0], or NULL = 1 (`ttl_loss.backward()`). Gradients go to each segment's
+ * gp1 / gp2 (NULL = not requested). */
+int fpsg_chamfer_multi_loss_fwd_bwd(const fpsg_chamfer_segment_t* segs_host, int nseg, int N, int M, float w1,
+                                    float w2, const float* gtotal, float* loss, float* totals, int64_t* idx1,
+                                    int64_t* idx2, void* ws, size_t ws_bytes, fpsg_stream_t stream);
+
+/* Diagnostics: byte offset, inside a workspace of fpsg_chamfer_fwd_workspace_bytes(B, N, M), of a 32-bit counter
+ * that every Chamfer forward zeroes and then increments once per point whose arg-min recovery found no candidate
+ * bit-equal to its merged minimum (the kernels then fall back to the first candidate). It must read 0 after any
+ * call; the parity tests assert that. */
+size_t fpsg_chamfer_ws_diag_offset(int B, int N, int M);
+
+/* Non-finite inputs (all Chamfer entry points): a distance that evaluates to NaN is skipped, as by the strict-'<'
+ * scan of the reference kernel; a point without any finite distance (NaN / Inf coordinates, or an all-NaN other
+ * cloud) gets dist = +INF and idx = 0, what that scan yields when started from +INF. The backward clamps indices
+ * to the valid range before gathering, so a caller-supplied idx tensor cannot cause out-of-bounds reads. */
 
 /* ---- kNN graph ------------------------------------------------------------------------------------------ */
 /* x (B,C,N) channel-major FP32; idx (B,N,k) int64: the k nearest points of every point (self included),
