@@ -4,7 +4,9 @@ bench.py uses. Usage: step_c1.py [B N M]"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from fpsg_b200 import _lib
+from fpsg_b200 import _lib, build
+if os.environ.get("FPSG_TUNING_LIB"):   # the development build, so that the FPSG_* ablation switches take effect
+    _lib.use_library(build.LIB_TUNING)
 from bench import make_inputs
 
 L = _lib.lib()

@@ -58,6 +58,19 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_chamfer_loss_fwd_bwd.argtypes = [vp, vp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp]
     L.fpsg_chamfer_multi_loss_fwd_bwd.restype = c_int
     L.fpsg_chamfer_multi_loss_fwd_bwd.argtypes = [segp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, vp, c_size_t, vp]
+    szp, vpp = ctypes.POINTER(c_size_t), ctypes.POINTER(vp)
+    L.fpsg_chamfer_pipeline_arena_bytes.restype = c_int
+    L.fpsg_chamfer_pipeline_arena_bytes.argtypes = [c_int, c_int, c_int, c_int, szp, szp]
+    L.fpsg_chamfer_pipeline_create.restype = c_int
+    L.fpsg_chamfer_pipeline_create.argtypes = [c_int, c_int, c_int, c_float, c_float, c_int, vp, c_size_t, vp, c_size_t, vpp]
+    L.fpsg_chamfer_pipeline_submit.restype = c_int
+    L.fpsg_chamfer_pipeline_submit.argtypes = [vp, vp, vp]
+    L.fpsg_chamfer_pipeline_result.restype = c_int
+    L.fpsg_chamfer_pipeline_result.argtypes = [vp, ctypes.POINTER(c_float), vp, vpp, vpp, vpp]
+    L.fpsg_chamfer_pipeline_compute_stream.restype = vp
+    L.fpsg_chamfer_pipeline_compute_stream.argtypes = [vp]
+    L.fpsg_chamfer_pipeline_destroy.restype = c_int
+    L.fpsg_chamfer_pipeline_destroy.argtypes = [vp]
     L.fpsg_chamfer_ws_diag_offset.restype = c_size_t
     L.fpsg_chamfer_ws_diag_offset.argtypes = [c_int, c_int, c_int]
     L.fpsg_knn_workspace_bytes.restype = c_size_t
@@ -80,14 +93,26 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_probe_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]
 
 
+_path = LIB
+
+
+def use_library(path: str) -> None:
+    """Development hook (bench_micro/): load another build of the library -- the tuning variant with its ablation switches and
+    timeline stamps -- instead of the product one. Must be called before the first use."""
+    global _path
+    if _lib is not None:
+        raise FpsgError("use_library() must be called before the library is first used")
+    _path = path
+
+
 def lib() -> ctypes.CDLL:
     """The loaded library. Raises if it has not been built: the product never runs without its CUDA code."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            raise FpsgError(f"{LIB} is missing: build it with `python fpsg_b200/build.py` "
+        if not os.path.exists(_path):
+            raise FpsgError(f"{_path} is missing: build it with `python fpsg_b200/build.py` "
                             "(fpsg_b200 has no CPU or PyTorch fallback)")
-        L = ctypes.CDLL(LIB)
+        L = ctypes.CDLL(_path)
         _declare(L)
         got = L.fpsg_abi_version()
         if got != ABI_VERSION:

@@ -9,7 +9,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfpsg_b200.so")
-SOURCES = ["api.cu", "chamfer_fwd.cu", "chamfer_finish.cu", "chamfer_bwd.cu", "knn.cu", "edge_feature.cu", "pointcloud_io.cu"]
+LIB_TUNING = os.path.join(HERE, "libfpsg_b200_tuning.so")  # development build: FPSG_* ablation switches + timeline stamps
+SOURCES = ["api.cu", "chamfer_fwd.cu", "chamfer_finish.cu", "chamfer_bwd.cu", "pipeline.cu", "knn.cu", "edge_feature.cu", "pointcloud_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-cudart", "static", "-diag-suppress", "550"]
 
@@ -29,19 +30,21 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, tuning: bool = False) -> str:
+    """tuning=True builds the development variant (-DFPSG_TUNING: the FPSG_* ablation switches and the timeline stamps used by
+    bench_micro/) as a separate file; the product library never contains them."""
+    out = LIB_TUNING if tuning else LIB
+    if not force and not tuning and not is_stale():
         return LIB
-    tuning = ["-DFPSG_TUNING"] if os.environ.get("FPSG_BUILD_TUNING") else []  # FPSG_* ablation switches (bench_micro/) compiled in
-    cmd = [_nvcc()] + NVCC_FLAGS + tuning + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-DFPSG_TUNING"] if tuning else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
     import sys
-    print(build_library(force=True, verbose="-v" in sys.argv))
+    print(build_library(force=True, verbose="-v" in sys.argv, tuning="--tuning" in sys.argv))

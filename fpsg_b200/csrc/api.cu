@@ -16,6 +16,9 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+static unsigned long long* g_trace = nullptr;
+unsigned long long* trace_buffer() { return g_trace; }
+
 // implemented in chamfer_fwd.cu / chamfer_bwd.cu / knn.cu
 size_t chamfer_forward_workspace(int B, int N, int M);
 int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
@@ -92,6 +95,15 @@ __global__ void __launch_bounds__(512) fp32_peak_kernel(float* out, long long* c
 using namespace fpsg;
 
 extern "C" {
+
+#ifdef FPSG_TUNING
+// tuning builds only (not declared in include/fpsg_b200.h): device buffer of 4 * kTraceCtas * kTracePhases u64 for the
+// kernels' timeline stamps, or NULL to switch them off
+int fpsg_tune_set_trace(void* buf) {
+    g_trace = static_cast<unsigned long long*>(buf);
+    return FPSG_OK;
+}
+#endif
 
 int fpsg_abi_version(void) { return FPSG_ABI_VERSION; }
 

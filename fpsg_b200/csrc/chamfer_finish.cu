@@ -32,9 +32,9 @@ namespace cg = cooperative_groups;
 
 namespace fpsg {
 
-constexpr int kFinishCluster = 8;
+constexpr int kFinishClusterMax = 8;  // CTAs per pair (= cluster size)
 constexpr int kBucket = 4;           // inverted-index entries held per point; longer buckets spill to the overflow list
-constexpr int kFinishMaxPoints = 4096;  // per cloud: one row and one column per thread, 512 worker threads per CTA
+constexpr int kFinishMaxPoints = 4096;  // per cloud: one row and one column per thread, up to 512 threads per CTA
 
 struct FinishArgs {
     SegTable seg;
@@ -56,6 +56,8 @@ struct FinishArgs {
     int B;
     int rpcN, rpcM;  // rows / columns per CTA (multiples of 32)
     int N32, M32;    // cloud sizes rounded up to whole 32-point windows
+    const unsigned* progress;   // the sweep CTAs' progress words (chamfer_plan.cuh)
+    unsigned long long* trace;  // timeline stamps (tuning builds), else nullptr
 };
 
 struct FinishSmem {
@@ -85,7 +87,7 @@ static FinishSmem finish_smem_layout(int N, int M, int rpcN, int rpcM, bool want
     L.misc = off;  // [0] overflow count side 1, [1] overflow count side 2
     off += 16;
     L.loss = off;  // [cluster rank][warp][2] doubles (used in rank 0)
-    off += (size_t)kFinishCluster * nwarps * 2 * sizeof(double);
+    off += (size_t)kFinishClusterMax * nwarps * 2 * sizeof(double);
     L.total = off;
     return L;
 }
@@ -98,7 +100,7 @@ __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 template <bool kWant2>
-__global__ void __launch_bounds__(kFinishMaxPoints / kFinishCluster + 32, 1) chamfer_finish_kernel(const FinishArgs a, const FinishSmemOff so) {
+__global__ void __launch_bounds__(kFinishMaxPoints / kFinishClusterMax + 64, 2) chamfer_finish_kernel(const FinishArgs a, const FinishSmemOff so) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* sP2 = reinterpret_cast<float*>(smem + so.p2);
     float* sP1 = reinterpret_cast<float*>(smem + so.p1);
@@ -112,11 +114,14 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishCluster + 32, 1) cha
     double* sLoss = reinterpret_cast<double*>(smem + so.loss);
 
     cg::cluster_group cluster = cg::this_cluster();
-    const int rank = blockIdx.x;  // cluster dimension = (kFinishCluster, 1, 1) = the grid's x extent
+    const int rank = blockIdx.x, kFinishCluster = gridDim.x;  // cluster dimension = (gridDim.x, 1, 1)
     const int b = blockIdx.y;
-    const int nthreads = blockDim.x, T = nthreads - 32;  // T worker threads + one extra warp for the reductions
+    // Register budget: 64 per thread, so that a 256-thread CTA (c1: 2048-point clouds) needs 2 warps x 2048 registers per SM
+    // sub-partition -- exactly what ONE retiring sweep CTA (4 warps x 128 threads x 128 registers) frees there. The finish
+    // CTAs then become resident, stage their clouds and start polling while the rest of the sweep is still running.
+    const int nthreads = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nwarps = nthreads >> 5;
-    const bool worker = tid < T;
+    constexpr bool worker = true;
 
     const int sg = a.seg.n == 1 ? 0 : seg_find(a.seg, b);
     const int bl = b - a.seg.b0[sg];
@@ -176,7 +181,13 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishCluster + 32, 1) cha
     const float u1 = __fmul_rn(2.0f, __fdiv_rn(__fmul_rn(gl, a.w1), (float)a.N));
     const float u2 = __fmul_rn(2.0f, __fdiv_rn(__fmul_rn(gl, a.w2), (float)a.M));
 
-    cudaGridDependencySynchronize();  // the sweep's partials are complete and visible from here on
+    // Not cudaGridDependencySynchronize(): the CTA waits for the sweep CTAs that cover ITS pair only (their progress
+    // words, zeroed before this grid could launch). Units are pair-major over the sweep CTAs and an SM retires its
+    // resident sweep CTAs one after the other, so the early pairs are finished -- merge, arg-min, loss, backward -- while
+    // the sweep is still working on the late ones, in the issue slots the sweep leaves free.
+    FPSG_TRACE(a.trace, 1, b * kFinishCluster + rank, 0);
+    wait_pair_swept(a.progress, b, a.strips * a.ups, a.q, a.r);
+    FPSG_TRACE(a.trace, 1, b * kFinishCluster + rank, 1);
 
     // ---- 1. merges: the column records of strip 0 are put in flight first, then the row minima (24 per round trip), so
     // that both directions share one L2 latency ----
@@ -218,6 +229,7 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishCluster + 32, 1) cha
 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();  // staged clouds visible to the whole CTA
+    FPSG_TRACE(a.trace, 1, b * kFinishCluster + rank, 2);
 
     // ---- 2. arg-min recovery: thread-private scan of the candidates' window, visited in a lane-dependent rotation
     // (windows start on multiples of 32 points = 96 floats: un-rotated all lanes would hit the same bank); the lowest
@@ -261,6 +273,7 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishCluster + 32, 1) cha
     }
 
     // ---- 3. inverted index through distributed shared memory ----
+    FPSG_TRACE(a.trace, 1, b * kFinishCluster + rank, 3);
     cluster_wait_acquire();  // barrier #1: every CTA of the cluster is running and has zeroed its counters (long ago)
     if (lane == 0 && worker) {
         double* dst = cluster.map_shared_rank(sLoss, 0) + ((size_t)rank * nwarps + w) * 2;
@@ -289,47 +302,27 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishCluster + 32, 1) cha
     }
     cluster_arrive_release();  // barrier #2: buckets and loss partials of the whole pair are complete
     cluster_wait_acquire();
+    FPSG_TRACE(a.trace, 1, b * kFinishCluster + rank, 4);
 
-    // ---- 4a. the extra warp of rank 0: loss of the pair, batch-level sums ----
-    if (!worker) {
-        if (rank == 0) {
-            double s1 = 0.0, s2 = 0.0;
-            const int nent = kFinishCluster * nwarps;
-            for (int e = lane; e < nent; e += 32) {
-                if ((e % nwarps) < nwarps - 1) {  // worker warps only
-                    s1 += sLoss[2 * e];
-                    s2 += sLoss[2 * e + 1];
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s1 += __shfl_down_sync(0xffffffffu, s1, o);
-                s2 += __shfl_down_sync(0xffffffffu, s2, o);
-            }
-            if (lane == 0) a.loss[b] = (float)((double)a.w1 * (s1 / a.N) + (double)a.w2 * (s2 / a.M));
-            if (a.totals) {
-                // the reduction on top (few_shot.py:110,117,121): whichever pair finishes last adds the per-pair losses in
-                // index order, per segment, in double -- independent of arrival order
-                bool last = false;
-                if (lane == 0) last = arrive_acq_rel(a.counters + a.B) == (unsigned)(a.B - 1);  // publishes loss[b]
-                if (__shfl_sync(0xffffffffu, last, 0)) {
-                    __syncwarp();
-                    const volatile float* lv = a.loss;
-                    double total = 0.0;
-                    for (int s = 0; s < a.seg.n; ++s) {
-                        double acc = 0.0;
-                        for (int q = a.seg.b0[s] + lane; q < a.seg.b0[s + 1]; q += 32) acc += (double)lv[q];
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-                        acc = __shfl_sync(0xffffffffu, acc, 0);
-                        if (lane == 0) a.totals[1 + s] = (float)acc;
-                        total += (double)a.seg.weight[s] * (double)(float)acc;
-                    }
-                    if (lane == 0) a.totals[0] = (float)total;
-                }
-            }
+    // ---- 4a. warp 0 of rank 0: loss of the pair (fixed order: independent of arrival order); for the batch-level sums it
+    // only ISSUES its arrival here -- the atomic's round trip hides behind the backward, its result is looked at in 4c ----
+    unsigned tot_ticket = 0u;
+    if (w == 0 && rank == 0) {
+        double s1 = 0.0, s2 = 0.0;
+        const int nent = kFinishCluster * nwarps;
+        for (int e = lane; e < nent; e += 32) {
+            s1 += sLoss[2 * e];
+            s2 += sLoss[2 * e + 1];
         }
-        return;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_down_sync(0xffffffffu, s1, o);
+            s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            a.loss[b] = (float)((double)a.w1 * (s1 / a.N) + (double)a.w2 * (s2 / a.M));
+            if (a.totals) tot_ticket = arrive_acq_rel(a.counters + a.B);  // publishes loss[b]
+        }
     }
 
     // ---- 4b. backward: direct edge + bucket, gathered from the staged clouds, accumulated in double ----
@@ -411,6 +404,26 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishCluster + 32, 1) cha
             o[2] = (float)gz;
         }
     }
+    // ---- 4c. the reduction on top (few_shot.py:110,117,121): whichever pair arrived last adds the per-pair losses in index
+    // order, per segment, in double -- independent of arrival order ----
+    if (w == 0 && rank == 0 && a.totals) {
+        if (__shfl_sync(0xffffffffu, tot_ticket, 0) == (unsigned)(a.B - 1)) {
+            __syncwarp();
+            const volatile float* lv = a.loss;
+            double total = 0.0;
+            for (int s = 0; s < a.seg.n; ++s) {
+                double acc = 0.0;
+                for (int q = a.seg.b0[s] + lane; q < a.seg.b0[s + 1]; q += 32) acc += (double)lv[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+                acc = __shfl_sync(0xffffffffu, acc, 0);
+                if (lane == 0) a.totals[1 + s] = (float)acc;
+                total += (double)a.seg.weight[s] * (double)(float)acc;
+            }
+            if (lane == 0) a.totals[0] = (float)total;
+        }
+    }
+    FPSG_TRACE(a.trace, 1, b * kFinishCluster + rank, 5);
 }
 
 bool chamfer_finish_supported(int N, int M) { return N <= kFinishMaxPoints && M <= kFinishMaxPoints; }
@@ -436,22 +449,34 @@ int chamfer_finish_launch(const SegTable& seg, const ChamferPlan& pl, int B, int
     fa.dist1 = dist1, fa.dist2 = dist2, fa.idx1 = idx1, fa.idx2 = idx2;
     fa.counters = reinterpret_cast<unsigned*>(base + pl.counters_off);
     fa.loss = loss, fa.w1 = w1, fa.w2 = w2, fa.totals = totals, fa.gloss = gloss, fa.gtotal = gtotal, fa.multi = multi ? 1 : 0, fa.B = B;
+    // CTAs per pair = cluster size: 8 CTAs of up to 512 threads. (Measured alternatives at c1, bench_micro/run_r02h.sh: 4 CTAs
+    // of 512 threads 59.0 us, 4 CTAs alone on their SMs 59.3 us, 8 CTAs alone on their SMs 70.8 us, against 56.4 us. The
+    // hardware places the CTAs of a cluster depth-first, so a finish CTA becomes resident only once its SM has two or three
+    // free sweep slots -- 33-40 us into a 43-us sweep -- whatever its own footprint.)
+    int cl = kFinishClusterMax;
+    if (const char* e = tune_env("FPSG_FINISH_CL")) cl = atoi(e) == 4 ? 4 : 8;
+    const int kFinishCluster = cl;
     fa.rpcN = (int)align_up((size_t)cdiv(N, kFinishCluster), 32);
     fa.rpcM = (int)align_up((size_t)cdiv(M, kFinishCluster), 32);
     fa.N32 = (int)align_up((size_t)N, 32);
     fa.M32 = (int)align_up((size_t)M, 32);
-    const int T = fa.rpcN > fa.rpcM ? fa.rpcN : fa.rpcM;
-    const int threads = T + 32;
+    fa.progress = reinterpret_cast<const unsigned*>(base + pl.progress_off);
+    fa.trace = trace_buffer();
+    const int threads = fa.rpcN > fa.rpcM ? fa.rpcN : fa.rpcM;
     const FinishSmem L = finish_smem_layout(N, M, fa.rpcN, fa.rpcM, want2, threads / 32);
     const FinishSmemOff so{(unsigned)L.p2, (unsigned)L.p1, (unsigned)L.cnt1, (unsigned)L.bkt1, (unsigned)L.ovf1, (unsigned)L.cnt2, (unsigned)L.bkt2,
                            (unsigned)L.ovf2, (unsigned)L.misc, (unsigned)L.loss};
     auto kern = want2 ? chamfer_finish_kernel<true> : chamfer_finish_kernel<false>;
-    if (L.total > 48 * 1024)  // per-device opt-in, repeated per launch like the other kernels' (about a microsecond of host time)
-        FPSG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    size_t smem_req = L.total;
+    bool one_per_sm = false;
+    if (const char* e = tune_env("FPSG_FINISH_PAD")) one_per_sm = atoi(e) != 0;  // tuning build only
+    if (one_per_sm && smem_req < 116 * 1024) smem_req = 116 * 1024;  // more than half an SM's shared memory: one CTA per SM
+    if (smem_req > 48 * 1024)  // per-device opt-in, repeated per launch like the other kernels' (about a microsecond of host time)
+        FPSG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kFinishCluster, (unsigned)B);
     cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = L.total;
+    cfg.dynamicSmemBytes = smem_req;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

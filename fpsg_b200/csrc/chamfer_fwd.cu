@@ -38,6 +38,7 @@
 namespace fpsg {
 
 static int g_sm_count = 0;
+constexpr int kSweepCarveoutPercent = 72;  // 164 KB of 228
 
 int sm_count() {
     if (g_sm_count == 0) {
@@ -103,6 +104,8 @@ ChamferPlan make_chamfer_plan(int B, int N, int M) {
     off += align_up((size_t)B * (p.nrb + p.ncb) * sizeof(double), 256);
     p.counters_off = off;
     off += align_up(((size_t)B + kExtraCounters) * sizeof(unsigned), 256);
+    p.progress_off = off;
+    off += align_up((size_t)p.grid * sizeof(unsigned), 256);
     p.total_bytes = off;
     return p;
 }
@@ -141,9 +144,23 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R)) chamfer_s
     float pf[kPf];    // the next piece's tile, in flight from global memory during the current piece
 
     cudaGridDependencySynchronize();  // (PDL) the producer of p1/p2 and the previous user of the workspace are done
+    FPSG_TRACE(a.trace, 0, g, 0);
+#ifdef FPSG_TUNING
+    if (a.trace != nullptr && tid == 0 && g < kTraceCtas) {  // where this CTA runs: (SM id, warp slot of its warp 0)
+        unsigned sm, wid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        a.trace[((size_t)g) * kTracePhases + 3] = ((u64)sm << 32) | wid;
+    }
+#endif
     if (g == 0)
         for (int q = tid; q < a.B + kExtraCounters; q += kSweepThreads) a.counters[q] = 0u;
-    // let the next grid of the chain be scheduled onto SMs as this grid's CTAs retire (it waits for our completion itself)
+    if (tid == 0) a.progress[g] = 0u;
+    // The next grid of the chain may be scheduled onto SMs as this grid's CTAs retire. It is launched once EVERY CTA of
+    // this grid has passed the trigger, i.e. after all counters and progress words were zeroed and fenced: a consumer that
+    // polls the progress words (chamfer_finish.cu) can never see a stale value of an earlier launch.
+    __threadfence();
+    __syncthreads();
     cudaTriggerProgrammaticLaunchCompletion();
 
     auto fetch = [&](int bs_, int cu_, int n_) {  // global -> registers; INF beyond the piece: padded columns never win
@@ -284,6 +301,13 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R)) chamfer_s
                 dm[k >> 2] = make_float4(best[k], best[k + 1], best[k + 2], best[k + 3]);
                 ds[k >> 2] = make_int4(sSubIdx[k][tid], sSubIdx[k + 1][tid], sSubIdx[k + 2][tid], sSubIdx[k + 3][tid]);
             }
+        }
+        // last piece of a PAIR for this CTA: publish how far the run has come (all of the CTA's stores so far, then one
+        // release store)
+        if (nleft == 0 || (a.strips == 1 ? nbs : nbs / a.strips) != b) {
+            __syncthreads();
+            if (tid == 0) st_release_u32(a.progress + g, (unsigned)(a.q + (g < a.r ? 1 : 0) - nleft));
+            FPSG_TRACE(a.trace, 0, g, nleft == 0 ? 2 : 1);
         }
         bs = nbs;
         cu = ncu;
@@ -616,8 +640,24 @@ int chamfer_sweep_launch(const SegTable& seg, const ChamferPlan& pl, int B, int 
     char* base = static_cast<char*>(ws);
     const SweepArgs sa{seg, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, reinterpret_cast<float*>(base + pl.rowmin_off),
                        reinterpret_cast<int*>(base + pl.rowsub_off), reinterpret_cast<u64*>(base + pl.colpart_off),
-                       reinterpret_cast<unsigned*>(base + pl.counters_off), B};
+                       reinterpret_cast<unsigned*>(base + pl.counters_off), B, reinterpret_cast<unsigned*>(base + pl.progress_off),
+                       trace_buffer()};
     const dim3 sgrid((unsigned)pl.grid), sblock(kSweepThreads);
+    // Shared-memory carve-out: the sweep itself needs 76 KB per SM, for which the driver would configure 100 KB -- and the
+    // kernel that follows it in the chain (finalize / finish: 25-60 KB per CTA, staged ahead of its dependency wait) could
+    // then not become co-resident before most of the SM's sweep CTAs have retired (measured: resident at 33 us instead of
+    // 28 us of a 42-us sweep). The sweep asks for 164 of the 228 KB (all of it costs the sweep 1.8 us: its tile prefetches hit in L1).
+    {
+        static bool done[64] = {};  // per device; a benign race: the attribute is idempotent
+        int dev = 0;
+        FPSG_CUDA_OK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            FPSG_CUDA_OK(cudaFuncSetAttribute(chamfer_sweep_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, kSweepCarveoutPercent));
+            FPSG_CUDA_OK(cudaFuncSetAttribute(chamfer_sweep_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, kSweepCarveoutPercent));
+            FPSG_CUDA_OK(cudaFuncSetAttribute(chamfer_sweep_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, kSweepCarveoutPercent));
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+    }
     if (pl.R == 16)
         FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<16>, sgrid, sblock, 0, stream, sa));
     else if (pl.R == 8)

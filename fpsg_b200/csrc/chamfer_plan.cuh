@@ -28,12 +28,17 @@ struct ChamferPlan {
     int Mpad;         // M rounded up to a unit
     int fin_threads;  // threads per finalize CTA
     int nrb, ncb;     // finalize CTAs per pair: row blocks, column blocks
-    size_t rowmin_off, rowsub_off, colpart_off, losspart_off, counters_off, total_bytes;
+    size_t rowmin_off, rowsub_off, colpart_off, losspart_off, counters_off, progress_off, total_bytes;
 };
 
 // counters region of the workspace: [0, B) per-pair arrival counters, [B] batch-level arrival counter,
 // [B + 1] diagnostic: arg-min recoveries that found no candidate equal to the merged minimum (must stay 0)
 constexpr int kExtraCounters = 2;
+// progress region: one word per sweep CTA = the units of its run it has completed AND published. Every sweep CTA zeroes
+// its own word before it lets the next grid of the chain launch (the launch-completion trigger), so a consumer that was
+// launched programmatically behind the sweep can poll the words of the CTAs that cover its pair instead of waiting for
+// the whole sweep grid (chamfer_finish.cu): pairs are laid out pair-major over the CTAs and the hardware retires the
+// resident CTAs of an SM one after the other, so most pairs are complete long before the grid is.
 
 ChamferPlan make_chamfer_plan(int B, int N, int M);
 int sm_count();
@@ -47,6 +52,8 @@ struct SweepArgs {
     u64* colpart;   // [B*strips][4 warps][Mpad]  (min bits << 32) | ballot of lanes attaining it
     unsigned* counters;  // [B + kExtraCounters], zeroed by the sweep kernel
     int B;
+    unsigned* progress;         // [grid] see above
+    unsigned long long* trace;  // timeline stamps (tuning builds), else nullptr
 };
 
 #ifdef __CUDACC__
@@ -63,6 +70,33 @@ __device__ __forceinline__ unsigned arrive_acq_rel(unsigned* counter) {
     unsigned old;
     asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
     return old;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// first unit and number of units of sweep CTA g under the q/r partition
+__device__ __forceinline__ int cta_first_unit(int g, int q, int r) { return g * q + min(g, r); }
+
+// Blocks (warp 0 polls, then a CTA barrier) until every sweep CTA that covers pair b has published the units of that
+// pair: acquire loads of the progress words, one CTA per lane.
+__device__ __forceinline__ void wait_pair_swept(const unsigned* progress, int b, int upp, int q, int r) {
+    if (threadIdx.x < 32) {
+        const int u0 = b * upp, u1 = u0 + upp;  // the pair's units
+        const int g0 = cta_of_unit(u0, q, r), g1 = cta_of_unit(u1 - 1, q, r);
+        for (int g = g0 + (int)threadIdx.x; g <= g1; g += 32) {
+            const int s = cta_first_unit(g, q, r);
+            const unsigned need = (unsigned)(min(s + q + (g < r ? 1 : 0), u1) - s);
+            while (ld_acquire_u32(progress + g) < need) __nanosleep(20);
+        }
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ float warp_min_f32(float v) {

@@ -31,6 +31,27 @@ inline const char* tune_env(const char* name) { return std::getenv(name); }
 inline const char* tune_env(const char*) { return nullptr; }
 #endif
 
+// Timeline stamps (tuning builds only): kernels write %globaltimer values into a buffer registered with
+// fpsg_tune_set_trace (api.cu; not part of the product ABI), laid out [kernel][CTA][phase]. bench_micro/timeline.py
+// turns them into the step anatomy kept under profiles/.
+constexpr int kTraceCtas = 4096;
+constexpr int kTracePhases = 8;
+unsigned long long* trace_buffer();
+#if defined(FPSG_TUNING) && defined(__CUDACC__)
+#define FPSG_TRACE(ptr, kernel_id, cta, phase)                                                                   \
+    do {                                                                                                         \
+        if ((ptr) != nullptr && threadIdx.x == 0 && (cta) < ::fpsg::kTraceCtas) {                                \
+            unsigned long long t_;                                                                               \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                               \
+            (ptr)[((size_t)(kernel_id) * ::fpsg::kTraceCtas + (cta)) * ::fpsg::kTracePhases + (phase)] = t_;      \
+        }                                                                                                        \
+    } while (0)
+#else
+#define FPSG_TRACE(ptr, kernel_id, cta, phase) \
+    do {                                       \
+    } while (0)
+#endif
+
 constexpr size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 

@@ -1,0 +1,171 @@
+// Host-buffer streaming step: the shape of the reference's training loop around the loss
+// (reference src/trainNetwork.py:141-148: `to_cuda(sample)` -> `model.loss(sample)` -> `ttl_loss.backward()` -> `.item()`),
+// as a small native runtime on top of the fused loss step (chamfer_finish.cu).
+//
+//   submit(p1_host, p2_host) : enqueue the H2D copies of one batch on a COPY stream, then -- on the COMPUTE stream, behind an
+//                              event -- sweep + finish (loss, batch sum, gradient w.r.t. p1) and the D2H copy of the
+//                              batch's losses into pinned memory. Returns at once.
+//   result(...)              : waits for the oldest submitted batch (event), hands out its loss sum, its per-pair losses and
+//                              the device address of its gradient.
+//
+// With `depth` >= 2 slots the copies of batch i+1 run while batch i is being computed: the PCIe time of a batch (1.6 MB,
+// about 30 us) hides behind its predecessor's 56 us of kernels. The caller owns all memory -- one device arena and one
+// pinned host arena, sized by fpsg_chamfer_pipeline_arena_bytes -- the handle owns two streams and 2 x depth events.
+// A handle is used by one host thread at a time.
+#include <new>
+
+#include "common.cuh"
+
+namespace fpsg {
+
+size_t chamfer_forward_workspace(int B, int N, int M);
+int chamfer_fwd_bwd_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, float* loss,
+                           float* totals, float w1, float w2, const float* gloss, const float* gtotal, bool multi, void* ws, size_t ws_bytes,
+                           cudaStream_t stream, int mode);
+
+struct PipelineLayout {
+    size_t in_off, gp1_off, idx_off, out_off, slot_bytes;  // per slot (device)
+    size_t ws_off, ws_bytes, device_bytes;                 // shared workspace behind the slots
+    size_t out_bytes, pinned_bytes;                        // per-slot result record: totals[2] + loss[B]
+};
+
+static PipelineLayout pipeline_layout(int B, int N, int M, int depth) {
+    PipelineLayout L;
+    size_t off = 0;
+    L.in_off = off;
+    off += align_up((size_t)B * (N + M) * 3 * sizeof(float), 256);
+    L.gp1_off = off;
+    off += align_up((size_t)B * N * 3 * sizeof(float), 256);
+    L.idx_off = off;
+    off += align_up((size_t)B * (N + M) * sizeof(int64_t), 256);
+    L.out_off = off;
+    L.out_bytes = align_up((2 + (size_t)B) * sizeof(float), 256);
+    off += L.out_bytes;
+    L.slot_bytes = off;
+    L.ws_off = L.slot_bytes * depth;
+    L.ws_bytes = chamfer_forward_workspace(B, N, M);
+    L.device_bytes = L.ws_off + align_up(L.ws_bytes, 256);
+    L.pinned_bytes = L.out_bytes * depth;
+    return L;
+}
+
+}  // namespace fpsg
+
+using namespace fpsg;
+
+struct fpsg_chamfer_pipeline {
+    int B, N, M, depth;
+    float w1, w2;
+    PipelineLayout L;
+    char* dev;
+    char* pinned;
+    cudaStream_t copy, compute;
+    cudaEvent_t copied[8], done[8];
+    long long head, tail;  // batches submitted / results taken
+};
+
+extern "C" {
+
+int fpsg_chamfer_pipeline_arena_bytes(int B, int N, int M, int depth, size_t* device_bytes, size_t* pinned_host_bytes) {
+    if (B < 1 || N < 1 || M < 1 || depth < 1 || depth > 8) return fail(FPSG_EINVAL, "pipeline: need B, N, M >= 1 and 1 <= depth <= 8");
+    const PipelineLayout L = pipeline_layout(B, N, M, depth);
+    if (device_bytes) *device_bytes = L.device_bytes;
+    if (pinned_host_bytes) *pinned_host_bytes = L.pinned_bytes;
+    return FPSG_OK;
+}
+
+int fpsg_chamfer_pipeline_create(int B, int N, int M, float w1, float w2, int depth, void* device_arena, size_t device_bytes,
+                                 void* pinned_host_arena, size_t pinned_host_bytes, fpsg_chamfer_pipeline_t** out) {
+    if (!out) return fail(FPSG_EINVAL, "pipeline: null handle pointer");
+    *out = nullptr;
+    if (B < 1 || N < 1 || M < 1 || depth < 1 || depth > 8) return fail(FPSG_EINVAL, "pipeline: need B, N, M >= 1 and 1 <= depth <= 8");
+    if (B > 65535) return fail(FPSG_EINVAL, "pipeline: B > 65535 not supported");
+    const PipelineLayout L = pipeline_layout(B, N, M, depth);
+    if (!device_arena || device_bytes < L.device_bytes || (reinterpret_cast<uintptr_t>(device_arena) & 255) != 0)
+        return fail(FPSG_EWORKSPACE, "pipeline: a 256-byte aligned device arena of %zu bytes is required", L.device_bytes);
+    if (!pinned_host_arena || pinned_host_bytes < L.pinned_bytes)
+        return fail(FPSG_EWORKSPACE, "pipeline: a pinned host arena of %zu bytes is required", L.pinned_bytes);
+    fpsg_chamfer_pipeline* p = new (std::nothrow) fpsg_chamfer_pipeline();
+    if (!p) return fail(FPSG_EINVAL, "pipeline: out of host memory");
+    p->B = B, p->N = N, p->M = M, p->depth = depth, p->w1 = w1, p->w2 = w2, p->L = L;
+    p->dev = static_cast<char*>(device_arena);
+    p->pinned = static_cast<char*>(pinned_host_arena);
+    p->head = p->tail = 0;
+    p->copy = p->compute = nullptr;
+    for (int i = 0; i < 8; ++i) p->copied[i] = p->done[i] = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->compute, cudaStreamNonBlocking);
+    for (int i = 0; i < depth && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&p->copied[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        fpsg_chamfer_pipeline_destroy(p);
+        return fail(FPSG_ECUDA, "pipeline: stream / event creation failed: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return FPSG_OK;
+}
+
+int fpsg_chamfer_pipeline_submit(fpsg_chamfer_pipeline_t* p, const float* p1_host, const float* p2_host) {
+    if (!p || !p1_host || !p2_host) return fail(FPSG_EINVAL, "pipeline_submit: null argument");
+    if (p->head - p->tail >= p->depth) return fail(FPSG_EINVAL, "pipeline_submit: %d batches in flight, take a result first", p->depth);
+    const int s = (int)(p->head % p->depth);
+    char* slot = p->dev + (size_t)s * p->L.slot_bytes;
+    float* d1 = reinterpret_cast<float*>(slot + p->L.in_off);
+    float* d2 = d1 + (size_t)p->B * p->N * 3;
+    // the slot's inputs are free again once the step that last used them has run (its `done` event: the caller took that
+    // result before this slot could come round again, so the event is long complete -- the wait costs nothing)
+    if (p->head >= p->depth) FPSG_CUDA_OK(cudaStreamWaitEvent(p->copy, p->done[s], 0));
+    FPSG_CUDA_OK(cudaMemcpyAsync(d1, p1_host, (size_t)p->B * p->N * 3 * sizeof(float), cudaMemcpyHostToDevice, p->copy));
+    FPSG_CUDA_OK(cudaMemcpyAsync(d2, p2_host, (size_t)p->B * p->M * 3 * sizeof(float), cudaMemcpyHostToDevice, p->copy));
+    FPSG_CUDA_OK(cudaEventRecord(p->copied[s], p->copy));
+    FPSG_CUDA_OK(cudaStreamWaitEvent(p->compute, p->copied[s], 0));
+    float* gp1 = reinterpret_cast<float*>(slot + p->L.gp1_off);
+    int64_t* idx1 = reinterpret_cast<int64_t*>(slot + p->L.idx_off);
+    float* outrec = reinterpret_cast<float*>(slot + p->L.out_off);  // totals[2], then loss[B]
+    SegTable t = single_segment(d1, d2, gp1, nullptr, p->B);
+    const int rc = chamfer_fwd_bwd_launch(t, p->B, p->N, p->M, nullptr, nullptr, idx1, idx1 + (size_t)p->B * p->N, outrec + 2, outrec, p->w1, p->w2,
+                                          nullptr, nullptr, true, p->dev + p->L.ws_off, p->L.ws_bytes, p->compute, 0);
+    if (rc != FPSG_OK) return rc;
+    FPSG_CUDA_OK(cudaMemcpyAsync(p->pinned + (size_t)s * p->L.out_bytes, outrec, (2 + (size_t)p->B) * sizeof(float), cudaMemcpyDeviceToHost, p->compute));
+    FPSG_CUDA_OK(cudaEventRecord(p->done[s], p->compute));
+    ++p->head;
+    return FPSG_OK;
+}
+
+int fpsg_chamfer_pipeline_result(fpsg_chamfer_pipeline_t* p, float* loss_sum_host, float* loss_host, const float** gp1_device,
+                                 const int64_t** idx1_device, const int64_t** idx2_device) {
+    if (!p) return fail(FPSG_EINVAL, "pipeline_result: null handle");
+    if (p->tail >= p->head) return fail(FPSG_EINVAL, "pipeline_result: nothing in flight");
+    const int s = (int)(p->tail % p->depth);
+    FPSG_CUDA_OK(cudaEventSynchronize(p->done[s]));
+    const float* rec = reinterpret_cast<const float*>(p->pinned + (size_t)s * p->L.out_bytes);
+    if (loss_sum_host) *loss_sum_host = rec[0];
+    if (loss_host)
+        for (int b = 0; b < p->B; ++b) loss_host[b] = rec[2 + b];
+    char* slot = p->dev + (size_t)s * p->L.slot_bytes;
+    if (gp1_device) *gp1_device = reinterpret_cast<const float*>(slot + p->L.gp1_off);
+    if (idx1_device) *idx1_device = reinterpret_cast<const int64_t*>(slot + p->L.idx_off);
+    if (idx2_device) *idx2_device = reinterpret_cast<const int64_t*>(slot + p->L.idx_off) + (size_t)p->B * p->N;
+    ++p->tail;
+    return FPSG_OK;
+}
+
+fpsg_stream_t fpsg_chamfer_pipeline_compute_stream(fpsg_chamfer_pipeline_t* p) { return p ? static_cast<fpsg_stream_t>(p->compute) : nullptr; }
+
+int fpsg_chamfer_pipeline_destroy(fpsg_chamfer_pipeline_t* p) {
+    if (!p) return FPSG_OK;
+    if (p->compute) cudaStreamSynchronize(p->compute);
+    if (p->copy) cudaStreamSynchronize(p->copy);
+    for (int i = 0; i < 8; ++i) {
+        if (p->copied[i]) cudaEventDestroy(p->copied[i]);
+        if (p->done[i]) cudaEventDestroy(p->done[i]);
+    }
+    if (p->copy) cudaStreamDestroy(p->copy);
+    if (p->compute) cudaStreamDestroy(p->compute);
+    delete p;
+    return FPSG_OK;
+}
+
+}  // extern "C"

@@ -123,6 +123,31 @@ int fpsg_chamfer_multi_loss_fwd_bwd(const fpsg_chamfer_segment_t* segs_host, int
                                     float w2, const float* gtotal, float* loss, float* totals, int64_t* idx1,
                                     int64_t* idx2, void* ws, size_t ws_bytes, fpsg_stream_t stream);
 
+/* ---- Host-buffer streaming step ------------------------------------------------------------------------- */
+/* The reference's training loop around the loss (src/trainNetwork.py:141-148): `to_cuda(sample)`, `model.loss(sample)`,
+ * `ttl_loss.backward()`, `.item()` -- per batch: H2D copy of p1 (B,N,3) and p2 (B,M,3) from HOST memory (pinned memory
+ * makes the copies asynchronous), the fused loss step (fpsg_chamfer_multi_loss_fwd_bwd with one segment: per-pair loss,
+ * batch sum, gradient w.r.t. p1), D2H copy of the losses. `submit` only enqueues (copies on a copy stream, kernels on a
+ * compute stream, chained by events) and returns; `result` waits for the OLDEST submitted batch. With depth >= 2 the
+ * copies of batch i+1 overlap the kernels of batch i. Up to `depth` (1..8) batches may be in flight; the host buffers of
+ * a batch must stay valid until its result was taken. The caller owns all memory: a 256-byte aligned DEVICE arena and
+ * a PINNED HOST arena of the sizes fpsg_chamfer_pipeline_arena_bytes reports, both alive as long as the handle; the
+ * handle itself holds two CUDA streams and 2*depth events, and is used by one host thread at a time.
+ * result: *loss_sum_host = sum_b loss[b]; loss_host (B,) optional (NULL); *gp1_device / *idx1_device / *idx2_device
+ * (each optional) point INTO the device arena: gradient (B,N,3) and arg-min indices of that batch, complete when the
+ * call returns and valid until `depth` further batches have been submitted. */
+typedef struct fpsg_chamfer_pipeline fpsg_chamfer_pipeline_t;
+int fpsg_chamfer_pipeline_arena_bytes(int B, int N, int M, int depth, size_t* device_bytes, size_t* pinned_host_bytes);
+int fpsg_chamfer_pipeline_create(int B, int N, int M, float w1, float w2, int depth, void* device_arena,
+                                 size_t device_bytes, void* pinned_host_arena, size_t pinned_host_bytes,
+                                 fpsg_chamfer_pipeline_t** out);
+int fpsg_chamfer_pipeline_submit(fpsg_chamfer_pipeline_t* p, const float* p1_host, const float* p2_host);
+int fpsg_chamfer_pipeline_result(fpsg_chamfer_pipeline_t* p, float* loss_sum_host, float* loss_host,
+                                 const float** gp1_device, const int64_t** idx1_device, const int64_t** idx2_device);
+/* The stream the kernels of the pipeline run on (to order a consumer of gp1 behind them without a host round trip). */
+fpsg_stream_t fpsg_chamfer_pipeline_compute_stream(fpsg_chamfer_pipeline_t* p);
+int fpsg_chamfer_pipeline_destroy(fpsg_chamfer_pipeline_t* p);
+
 /* Diagnostics: byte offset, inside a workspace of fpsg_chamfer_fwd_workspace_bytes(B, N, M), of a 32-bit counter
  * that every Chamfer forward zeroes and then increments once per point whose arg-min recovery found no candidate
  * bit-equal to its merged minimum (the kernels then fall back to the first candidate). It must read 0 after any
