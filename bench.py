@@ -8,14 +8,15 @@
 Metric (BASELINE.json): Chamfer fwd+bwd pairs/s at B=32, N=M=2048 per GPU (weak scaling over 1/2/4/8 B200),
 plus the dominant kernel's fraction of the FP32 FMA roofline.
 
-A *step* = one pass of the hot path over one batch of 32 synthetic cloud pairs: fused Chamfer loss forward
-(sweep + finalize + loss kernels), backward to p1 (the ground truth has no gradient, as in the reference's
-training loss, src/models/few_shot.py:109-117), and -- for N > 1 -- the scalar loss all-reduce over NCCL.
+A *step* = one pass of the hot path over one batch of 32 synthetic cloud pairs: Chamfer loss forward and backward
+to p1 (the ground truth has no gradient, as in the reference's training loss, src/models/few_shot.py:109-117) as
+two kernels -- the sweep and the fused finish kernel (merge, arg-min, loss, batch sum, backward) -- and, for N > 1,
+the scalar loss all-reduce done inside the finish kernel's epilogue through NVLink peer memory, every step.
 
   value : whole-job pairs/s, inputs resident in HBM, the C ABI called directly, CUDA events, max over ranks.
-  e2e   : the same metric through the reference-facing Python call (the kaolin shim's
-          chamfer_distance(p1, p2).sum().backward()) with HOST (pinned) inputs: H2D copies and the D2H read of
-          the loss are inside the timed region.
+  e2e   : the same metric through the host-buffer call of the C ABI (fpsg_chamfer_pipeline_*): every step copies
+          its inputs from pinned HOST memory and reads its losses back; copies inside the timed region.
+          e2e_autograd: the reference-facing Python call (kaolin shim, torch.autograd), serial, for comparison.
   roofline     : the sweep kernel timed alone (fpsg_chamfer_sweep_only) against the FP32 FMA peak measured in
                  the same run by an FFMA micro-kernel (MEASURED_PEAKS.json has no FP32 row).
   cpu_baseline : the reference's PyTorch CPU formulation (oracle/torch_formulation.py) on a bounded sample.
@@ -40,8 +41,10 @@ B_PER_GPU, N_PTS, M_PTS = 32, 2048, 2048
 WORKLOAD = "c1: Chamfer loss fwd+bwd(p1), B=32 per GPU, N=M=2048, synthetic xyz float32"
 METRIC = "chamfer_fwd_bwd_pairs_per_s"
 RING_SETS = 96  # distinct input batches cycled through: 96 x 1.57 MB = 151 MB > 126 MB L2
-# dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch (profiles/r01b_chamfer_kernels_raw.csv, r01_summary.md)
+# dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch, from the ncu --set full capture named below (the
+# kernel streams its 1.573 MB of input once; a number taken under the profiler is cited, not re-measured in the timed run)
 SWEEP_DRAM_TRAFFIC_BYTES = 1.599e6
+SWEEP_DRAM_TRAFFIC_SOURCE = "profiles/r01g_chamfer_kernels_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, chamfer_sweep_kernel)"
 
 
 def make_inputs(batch, n, m, seed, device=None, pin=False):
@@ -174,7 +177,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": f"each step is a bounded sample of {sample} of the 32 pairs; value = pairs/s"},
+        "config": {"workload": f"{WORKLOAD}; reference arm: each step is a bounded sample of {sample} of the 32 pairs (value is a per-pair rate)",
+                   "sample_pairs_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample} pairs x {args.steps} steps of the c1 workload, pure-PyTorch difference-form Chamfer fwd+bwd "
                                    f"(oracle/torch_formulation.py; Kaolin 0.9.0 itself is absent), os.cpu_count()={os.cpu_count()}"},
@@ -184,6 +188,101 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def _timed_us(torch, stream, dev, fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(iters):
+        fn()
+    t1.record(stream)
+    torch.cuda.synchronize(dev)
+    return t0.elapsed_time(t1) / iters * 1e3
+
+
+def secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M):
+    """The other configurations of BASELINE.json (c2, c3, c4), device-resident inputs, the C ABI called directly. Not the
+    metric: reported for context, rank 0 only. Every Chamfer entry: us per call, pairs/s, fraction of the FP32 peak in the
+    16*N*M-FLOP-per-pair convention."""
+    sp = stream.cuda_stream
+    sec = {}
+
+    def chamfer_entry(us, pairs, n, m):
+        tf = 16.0 * pairs * n * m / us / 1e6
+        return {"us_per_call": us, "pairs_per_s": pairs / us * 1e6, "tflops": tf, "frac_of_fp32_peak": tf / fp32_peak_tflops}
+
+    # ---- c3: DGCNN kNN graph, k=20, B=32, N=1024: the xyz layer and the 64- / 128-channel layers (src/dgcnn/model.py:62-74)
+    gk = torch.Generator(device="cpu").manual_seed(1234 + 3)
+    for C_ in (3, 64, 128):
+        xk = torch.randn(32, C_, 1024, generator=gk).to(dev)
+        ik = torch.empty(32, 1024, 20, dtype=torch.int64, device=dev)
+        nbk = L.fpsg_knn_workspace_bytes(32, C_, 1024, 20)
+        wsk = torch.empty(max(nbk, 1), dtype=torch.uint8, device=dev)
+        us = _timed_us(torch, stream, dev, lambda: _lib.check(L.fpsg_knn_fwd(xk.data_ptr(), 32, C_, 1024, 20, ik.data_ptr(), wsk.data_ptr(), nbk, sp)), 20)
+        tf = (2 * C_ + 2) * 32 * 1024 * 1024 / us / 1e6
+        sec[f"c3_knn_k20_B32_N1024_C{C_}"] = {"us_per_call": us, "clouds_per_s": 32 / us * 1e6, "tflops": tf, "frac_of_fp32_peak": tf / fp32_peak_tflops}
+        del xk, ik, wsk
+
+    # ---- c2: one training step of 32 episodes = 32 x (5 query + 32 support) = 1184 pairs, N=M=2048
+    B2 = 1184
+    p1c2, p2c2 = make_inputs(B2, N, M, seed=1234 + 2, device=dev)
+    gp = torch.empty(B2, N, 3, device=dev)
+    ix = torch.empty(B2 * (N + M), dtype=torch.int64, device=dev)
+    lo = torch.empty(B2 + 4, device=dev)
+    nb2 = L.fpsg_chamfer_fwd_workspace_bytes(B2, N, M)
+    ws2 = torch.empty(nb2, dtype=torch.uint8, device=dev)
+    a2, b2, ip = p1c2.data_ptr(), p2c2.data_ptr(), ix.data_ptr()
+
+    def c2_one_call():
+        _lib.check(L.fpsg_chamfer_loss_fwd_bwd(a2, b2, B2, N, M, 1.0, 1.0, None, lo.data_ptr(), None, None, ip, ip + 8 * B2 * N, gp.data_ptr(), None,
+                                               ws2.data_ptr(), nb2, sp))
+    sec["c2_B1184_one_call"] = chamfer_entry(_timed_us(torch, stream, dev, c2_one_call, 10), B2, N, M)
+
+    def c2_as_issued():  # the reference's own call pattern: per episode a 5-pair call and a 32-pair call (few_shot.py:110,117)
+        for e in range(32):
+            o5, o32 = e * 37, e * 37 + 5
+            for off, nb_ in ((o5, 5), (o32, 32)):
+                _lib.check(L.fpsg_chamfer_loss_fwd_bwd(a2 + off * N * 12, b2 + off * M * 12, nb_, N, M, 1.0, 1.0, None, lo.data_ptr() + 4 * off, None, None,
+                                                       ip + 8 * off * N, ip + 8 * (B2 * N + off * M), gp.data_ptr() + off * N * 12, None,
+                                                       ws2.data_ptr(), nb2, sp))
+    sec["c2_B1184_as_64_calls"] = chamfer_entry(_timed_us(torch, stream, dev, c2_as_issued, 5, 2), B2, N, M)
+
+    sg2 = (_lib.ChamferSegment * 2)()
+    sg2[0].p1, sg2[0].p2, sg2[0].gp1, sg2[0].gp2, sg2[0].batch, sg2[0].weight = a2, b2, gp.data_ptr(), None, 5, 1.0
+    sg2[1].p1, sg2[1].p2, sg2[1].gp1, sg2[1].gp2 = a2 + 5 * N * 12, b2 + 5 * M * 12, gp.data_ptr() + 5 * N * 12, None
+    sg2[1].batch, sg2[1].weight = 32, 1.0
+
+    def episode_two_calls():
+        for off, nb_ in ((0, 5), (5, 32)):
+            _lib.check(L.fpsg_chamfer_loss_fwd_bwd(a2 + off * N * 12, b2 + off * M * 12, nb_, N, M, 1.0, 1.0, None, lo.data_ptr() + 4 * off, None, None,
+                                                   ip + 8 * off * N, ip + 8 * (B2 * N + off * M), gp.data_ptr() + off * N * 12, None, ws2.data_ptr(), nb2, sp))
+
+    def episode_one_call():
+        _lib.check(L.fpsg_chamfer_multi_loss_fwd_bwd(sg2, 2, N, M, 1.0, 1.0, None, lo.data_ptr() + 16, lo.data_ptr(), ip, ip + 8 * 37 * N,
+                                                     ws2.data_ptr(), nb2, sp))
+    sec["c2_episode_5q_32s"] = {"two_calls_us": _timed_us(torch, stream, dev, episode_two_calls, 50),
+                                "multi_segment_us": _timed_us(torch, stream, dev, episode_one_call, 50)}
+    del p1c2, p2c2, gp, ix, ws2
+
+    # ---- c4: large clouds, B=64, N=M in {4096, 8192, 16384}
+    for n4 in (4096, 8192, 16384):
+        B4 = 64
+        p1, p2 = make_inputs(B4, n4, n4, seed=1234 + 4, device=dev)
+        gp = torch.empty(B4, n4, 3, device=dev)
+        ix = torch.empty(B4 * 2 * n4, dtype=torch.int64, device=dev)
+        lo4 = torch.empty(B4, device=dev)
+        nb4 = L.fpsg_chamfer_fwd_workspace_bytes(B4, n4, n4)
+        ws4 = torch.empty(nb4, dtype=torch.uint8, device=dev)
+
+        def c4_call():
+            _lib.check(L.fpsg_chamfer_loss_fwd_bwd(p1.data_ptr(), p2.data_ptr(), B4, n4, n4, 1.0, 1.0, None, lo4.data_ptr(), None, None, ix.data_ptr(),
+                                                   ix.data_ptr() + 8 * B4 * n4, gp.data_ptr(), None, ws4.data_ptr(), nb4, sp))
+        sec[f"c4_B64_N{n4}"] = chamfer_entry(_timed_us(torch, stream, dev, c4_call, 10 if n4 < 16384 else 4, 2), B4, n4, n4)
+        del p1, p2, gp, ix, ws4
+    return sec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,6 +290,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU-baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the c2 / c3 / c4 / c5 context measurements")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -212,6 +312,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: fpsg_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    exchange = None
+    collective = "none (single GPU)"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner to stdout when the communicator is created (first collective); stdout must
@@ -224,6 +326,17 @@ def main():
             warm = torch.zeros(1, device=dev)
             dist.all_reduce(warm)
             torch.cuda.synchronize(dev)
+            # the scalar all-reduce of the path: done inside the loss kernel's epilogue through NVLink peer memory
+            # (fpsg_b200/sharded.py); torch.distributed only sets the tables up and reduces the timings at the end
+            from fpsg_b200.sharded import PeerScalarExchange
+            try:
+                exchange = PeerScalarExchange(dev)
+                collective = "per step, inside the loss kernel's epilogue through NVLink peer memory (lag 0: every step waits for all ranks' values)"
+            except Exception as exc:  # symmetric memory unavailable: NCCL, amortised, as in round 1
+                print(f"[bench] peer exchange unavailable ({exc!r}); falling back to NCCL all-reduce, 8 steps per collective", file=sys.stderr)
+                ok = torch.zeros(1, device=dev)
+                dist.all_reduce(ok)  # keep the ranks aligned
+                collective = "NCCL all-reduce, 8 steps per collective (peer exchange unavailable)"
         finally:
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
@@ -246,84 +359,82 @@ def main():
 
     # ---- inputs: a ring of distinct batches larger than L2, resident in HBM ----
     ring = [make_inputs(B, N, M, seed=1234 + 1 + 1000 * rank + s, device=dev) for s in range(RING_SETS)]
-    dist1 = torch.empty(B, N, device=dev)
-    dist2 = torch.empty(B, M, device=dev)
-    idx1 = torch.empty(B, N, dtype=torch.int64, device=dev)
-    idx2 = torch.empty(B, M, dtype=torch.int64, device=dev)
-    loss = torch.empty(B, device=dev)
+    idx = torch.empty(B * (N + M), dtype=torch.int64, device=dev)
+    out = torch.zeros(2 + B, device=dev)       # totals[2] (weighted total, segment sum), then the per-pair losses
     gloss = torch.ones(B, device=dev)
     gp1 = torch.empty(B, N, 3, device=dev)
-    # N > 1: the per-step sums of the local losses (logged values; the backward does not need them) are collected in a
-    # device-side ring of KLOG slots and all-reduced KLOG steps at a time -- torch.distributed's host-side cost of one
-    # collective (~45 us) would otherwise make the 64-us step host-bound. Two rings alternate.
-    KLOG = 8
-    totals = [torch.zeros(KLOG, 2, device=dev) for _ in range(2)]  # [:, 0] = sum over the local pairs of one step
-    pending = [None, None]
     nbytes = L.fpsg_chamfer_fwd_workspace_bytes(B, N, M)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
     ptrs = [(a.data_ptr(), b.data_ptr()) for a, b in ring]
-    o = (loss.data_ptr(), dist1.data_ptr(), dist2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), ws.data_ptr(), gloss.data_ptr(), gp1.data_ptr())
-
-    # N > 1: the local sum of the per-pair losses comes out of the finalize kernel itself (the one-segment form of
-    # fpsg_chamfer_multi_loss_fwd), so no reduction kernel sits between the forward and the backward
+    ip1, ip2 = idx.data_ptr(), idx.data_ptr() + 8 * B * N
     segs = []
     for a_, b_ in ptrs:
         sg = (_lib.ChamferSegment * 1)()
-        sg[0].p1, sg[0].p2, sg[0].gp1, sg[0].gp2, sg[0].batch, sg[0].weight = a_, b_, None, None, B, 1.0
+        sg[0].p1, sg[0].p2, sg[0].gp1, sg[0].gp2, sg[0].batch, sg[0].weight = a_, b_, gp1.data_ptr(), None, B, 1.0
         segs.append(sg)
-    tot_ptrs = [[t.data_ptr() + 8 * j for j in range(KLOG)] for t in totals]
+    KLOG = 8
+    nccl_ring = [torch.zeros(KLOG, 2, device=dev) for _ in range(2)]
+    pending = [None, None]
 
-    def step(i):
-        a, b = ptrs[i % RING_SETS]
-        if world == 1:
-            _lib.check(L.fpsg_chamfer_loss_fwd(a, b, B, N, M, 1.0, 1.0, o[0], o[1], o[2], o[3], o[4], o[5], nbytes, sp))
+    # One step = sweep + finish: per-pair losses, their sum over the local batch, the gradient w.r.t. p1 (the upstream
+    # gradient of `.sum()` / `ttl_loss.backward()` is the constant 1), and for N > 1 the scalar exchange -- two kernels.
+    def step(i, with_collective=True):
+        if world == 1 or not with_collective:
+            _lib.check(L.fpsg_chamfer_multi_loss_fwd_bwd(segs[i % RING_SETS], 1, N, M, 1.0, 1.0, None, out.data_ptr() + 8, out.data_ptr(), ip1, ip2,
+                                                         ws.data_ptr(), nbytes, sp))
+        elif exchange is not None:
+            _lib.check(L.fpsg_chamfer_multi_loss_fwd_bwd_dist(segs[i % RING_SETS], 1, N, M, 1.0, 1.0, None, out.data_ptr() + 8, out.data_ptr(), ip1, ip2,
+                                                              ws.data_ptr(), nbytes, exchange.next(0), sp))
         else:
             k, j = (i // KLOG) & 1, i % KLOG
             if j == 0 and pending[k] is not None:
-                # the all-reduce that last used this ring (KLOG steps ago) has normally finished long ago: a host-side
-                # query then suffices and no wait goes into the compute stream
                 if not pending[k].is_completed():
                     pending[k].wait()
                 pending[k] = None
-            _lib.check(L.fpsg_chamfer_multi_loss_fwd(segs[i % RING_SETS], 1, N, M, 1.0, 1.0, o[0], tot_ptrs[k][j], o[3], o[4], o[5], nbytes, sp))
-        _lib.check(L.fpsg_chamfer_loss_bwd(a, b, o[3], o[4], o[6], 1.0, 1.0, B, N, M, o[7], None, None, 0, sp))
-        if world > 1:
-            # issued after the backward launch: an event record between the finalize and the backward kernels would break
-            # their programmatic (PDL) chaining
+            _lib.check(L.fpsg_chamfer_multi_loss_fwd_bwd(segs[i % RING_SETS], 1, N, M, 1.0, 1.0, None, out.data_ptr() + 8,
+                                                         nccl_ring[k].data_ptr() + 8 * j, ip1, ip2, ws.data_ptr(), nbytes, sp))
             if j == KLOG - 1:
-                pending[k] = dist.all_reduce(totals[k], op=dist.ReduceOp.SUM, async_op=True)
+                pending[k] = dist.all_reduce(nccl_ring[k], op=dist.ReduceOp.SUM, async_op=True)
 
-    kernels_per_step = 3  # sweep, finalize (+ fused loss and batch sum), backward (the NCCL kernel for N > 1 is not ours)
+    kernels_per_step = 2  # sweep, finish (merge + arg-min + loss + batch sum + backward + scalar exchange)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def timed_steps(nsteps, with_collective=True):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        tw0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(nsteps):
+            step(args.warmup + i, with_collective)
+        e1.record(stream)
+        for k in (0, 1):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
+        barrier()
+        sampler.mark(tw0, time.perf_counter())
+        return e0.elapsed_time(e1)
+
     for i in range(args.warmup):
         step(i)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    tw0 = time.perf_counter()
-    e0.record(stream)
-    for i in range(args.steps):
-        step(args.warmup + i)  # same parity/ring phase as the warm-up left it
-    e1.record(stream)
-    for k in (0, 1):
-        if pending[k] is not None:
-            pending[k].wait()
-            pending[k] = None
-    barrier()
-    sampler.mark(tw0, time.perf_counter())
-    ms = e0.elapsed_time(e1)
+    ms = timed_steps(args.steps)
+    ms_nocoll = None
+    if world > 1:  # the same loop without the collective
+        for i in range(10):
+            step(i, False)
+        ms_nocoll = timed_steps(max(50, args.steps // 4), False) / max(50, args.steps // 4) * args.steps
 
     # ---- dominant kernel alone (roofline), same ring, same stream ----
     def sweep(i):
         a, b = ptrs[i % RING_SETS]
-        _lib.check(L.fpsg_chamfer_sweep_only(a, b, B, N, M, o[5], nbytes, sp))
+        _lib.check(L.fpsg_chamfer_sweep_only(a, b, B, N, M, ws.data_ptr(), nbytes, sp))
     for i in range(5):
         sweep(i)
     torch.cuda.synchronize(dev)
@@ -338,196 +449,179 @@ def main():
     sampler.mark(tw0, time.perf_counter())
     sweep_us = s0.elapsed_time(s1) / n_sweeps * 1e3
 
-    # ---- backward kernel alone (HBM view) ----
+    # ---- the separate backward kernel (autograd path), HBM view ----
     def bwd(i):
         a, b = ptrs[i % RING_SETS]
-        _lib.check(L.fpsg_chamfer_loss_bwd(a, b, o[3], o[4], o[6], 1.0, 1.0, B, N, M, o[7], None, None, 0, sp))
-    for i in range(5):
-        bwd(i)
-    torch.cuda.synchronize(dev)
-    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    b0.record(stream)
-    for i in range(n_sweeps):
-        bwd(5 + i)
-    b1.record(stream)
-    torch.cuda.synchronize(dev)
-    bwd_us = b0.elapsed_time(b1) / n_sweeps * 1e3
+        _lib.check(L.fpsg_chamfer_loss_bwd(a, b, ip1, ip2, gloss.data_ptr(), 1.0, 1.0, B, N, M, gp1.data_ptr(), None, None, 0, sp))
+    bwd_us = _timed_us(torch, stream, dev, lambda: bwd(0), n_sweeps, 5)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- secondary configurations of BASELINE.json (not the metric; reported for context, rank 0 only) ----
+    # ---- c5 (BASELINE.json configs[4]): STRONG scaling -- 256 pairs of 2048 points in total, sharded over the ranks,
+    # Chamfer loss step with the per-step scalar exchange, and the kNN graph (k=20, xyz) of the same 256 clouds ----
+    c5 = None
+    if not args.no_secondary:
+        B5 = 256 // world
+        p1s, p2s = make_inputs(B5, N, M, seed=1234 + 5 + 1000 * rank, device=dev)
+        gp5 = torch.empty(B5, N, 3, device=dev)
+        ix5 = torch.empty(B5 * (N + M), dtype=torch.int64, device=dev)
+        out5 = torch.zeros(2 + B5, device=dev)
+        nb5 = L.fpsg_chamfer_fwd_workspace_bytes(B5, N, M)
+        ws5 = torch.empty(nb5, dtype=torch.uint8, device=dev)
+        sg5 = (_lib.ChamferSegment * 1)()
+        sg5[0].p1, sg5[0].p2, sg5[0].gp1, sg5[0].gp2, sg5[0].batch, sg5[0].weight = p1s.data_ptr(), p2s.data_ptr(), gp5.data_ptr(), None, B5, 1.0
+
+        def c5_step():
+            if exchange is not None:
+                _lib.check(L.fpsg_chamfer_multi_loss_fwd_bwd_dist(sg5, 1, N, M, 1.0, 1.0, None, out5.data_ptr() + 8, out5.data_ptr(), ix5.data_ptr(),
+                                                                  ix5.data_ptr() + 8 * B5 * N, ws5.data_ptr(), nb5, exchange.next(0), sp))
+            else:
+                _lib.check(L.fpsg_chamfer_multi_loss_fwd_bwd(sg5, 1, N, M, 1.0, 1.0, None, out5.data_ptr() + 8, out5.data_ptr(), ix5.data_ptr(),
+                                                             ix5.data_ptr() + 8 * B5 * N, ws5.data_ptr(), nb5, sp))
+        xk5 = p2s.transpose(1, 2).contiguous()  # (B5, 3, 2048): the ground-truth clouds as the DGCNN encoder sees them
+        ik5 = torch.empty(B5, N, 20, dtype=torch.int64, device=dev)
+        nbk5 = L.fpsg_knn_workspace_bytes(B5, 3, N, 20)
+        wsk5 = torch.empty(max(nbk5, 1), dtype=torch.uint8, device=dev)
+
+        def c5_knn():
+            _lib.check(L.fpsg_knn_fwd(xk5.data_ptr(), B5, 3, N, 20, ik5.data_ptr(), wsk5.data_ptr(), nbk5, sp))
+        barrier()
+        t_ch = _timed_us(torch, stream, dev, c5_step, 30, 5)
+        barrier()
+        t_kn = _timed_us(torch, stream, dev, c5_knn, 10, 3)
+        barrier()
+        tt = torch.tensor([t_ch, t_kn], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ch, t_kn = float(tt[0]), float(tt[1])
+        c5 = {"scaling": "strong", "total_pairs": 256, "pairs_per_gpu": B5,
+              "chamfer_fwd_bwd": {"us_per_step_max_over_ranks": t_ch, "pairs_per_s": 256 / t_ch * 1e6,
+                                  "frac_of_fp32_peak_per_gpu": 16.0 * B5 * N * M / t_ch / 1e6 / fp32_peak_tflops},
+              "knn_k20_xyz_N2048": {"us_per_call_max_over_ranks": t_kn, "clouds_per_s": 256 / t_kn * 1e6},
+              "chamfer_plus_knn_pairs_per_s": 256 / (t_ch + t_kn) * 1e6}
+        del p1s, p2s, gp5, ix5, ws5, xk5, ik5, wsk5
+
     secondary = None
-    if rank == 0:
-        def timed(fn, iters=50, warm=5):
-            for _ in range(warm):
-                fn()
-            torch.cuda.synchronize(dev)
-            t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0_.record(stream)
-            for _ in range(iters):
-                fn()
-            t1_.record(stream)
-            torch.cuda.synchronize(dev)
-            return t0_.elapsed_time(t1_) / iters * 1e3
-        secondary = {}
-        gk = torch.Generator(device="cpu").manual_seed(1234 + 3)
-        for C_ in (3, 64):  # c3: DGCNN kNN graph, k=20, B=32, N=1024 (xyz layer; a 64-channel layer for scale)
-            xk = torch.randn(32, C_, 1024, generator=gk).to(dev)
-            ik = torch.empty(32, 1024, 20, dtype=torch.int64, device=dev)
-            nbk = L.fpsg_knn_workspace_bytes(32, C_, 1024, 20)
-            wsk = torch.empty(max(nbk, 1), dtype=torch.uint8, device=dev)
-            us = timed(lambda: _lib.check(L.fpsg_knn_fwd(xk.data_ptr(), 32, C_, 1024, 20, ik.data_ptr(), wsk.data_ptr(), nbk, sp)), 20, 3)
-            secondary[f"knn_k20_B32_N1024_C{C_}"] = {"us_per_call": us, "tflops": (2 * C_ + 2) * 32 * 1024 * 1024 / us / 1e6,
-                                                    "frac_of_fp32_peak": (2 * C_ + 2) * 32 * 1024 * 1024 / us / 1e6 / fp32_peak_tflops}
-            del xk, ik, wsk
-        # c2: one training episode (5 query + 32 support pairs) as the reference issues it (two calls) and as one call
-        qa, qb = ptrs[0]
-        sg2 = (_lib.ChamferSegment * 2)()
-        gp37 = torch.empty(37, N, 3, device=dev)
-        sg2[0].p1, sg2[0].p2, sg2[0].gp1, sg2[0].gp2, sg2[0].batch, sg2[0].weight = qa, qb, gp37.data_ptr(), None, 5, 1.0
-        sg2[1].p1, sg2[1].p2, sg2[1].gp1, sg2[1].gp2, sg2[1].batch, sg2[1].weight = (ptrs[1][0], ptrs[1][1], gp37.data_ptr() + 5 * N * 12, None,
-                                                                                   32, 1.0)
-        nb37 = L.fpsg_chamfer_fwd_workspace_bytes(37, N, M)
-        ws37 = torch.empty(nb37, dtype=torch.uint8, device=dev)
-        i37 = torch.empty(37 * (N + M), dtype=torch.int64, device=dev)
-        l37 = torch.empty(37 + 3, device=dev)
-        g1_ = torch.ones((), device=dev)
+    if rank == 0 and not args.no_secondary:
+        secondary = secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M)
+        secondary["c5_strong_B256"] = c5
+    if world > 1:
+        dist.barrier()
 
-        def two_calls():
-            for (a_, b_), nb_ in ((ptrs[0], 5), (ptrs[1], 32)):
-                _lib.check(L.fpsg_chamfer_loss_fwd(a_, b_, nb_, N, M, 1.0, 1.0, o[0], None, None, o[3], o[4], o[5], nbytes, sp))
-                _lib.check(L.fpsg_chamfer_loss_bwd(a_, b_, o[3], o[4], o[6], 1.0, 1.0, nb_, N, M, o[7], None, None, 0, sp))
-
-        def one_call():
-            _lib.check(L.fpsg_chamfer_multi_loss_fwd(sg2, 2, N, M, 1.0, 1.0, l37.data_ptr() + 12, l37.data_ptr(), i37.data_ptr(),
-                                                     i37.data_ptr() + 8 * 37 * N, ws37.data_ptr(), nb37, sp))
-            _lib.check(L.fpsg_chamfer_multi_loss_bwd(sg2, 2, i37.data_ptr(), i37.data_ptr() + 8 * 37 * N, g1_.data_ptr(), 1.0, 1.0, N, M, sp))
-        secondary["c2_episode_5q_32s"] = {"two_calls_us": timed(two_calls), "multi_segment_us": timed(one_call)}
-
-    # ---- end to end: the reference-facing call, host (pinned) inputs, loss read back every step ----
-    fpsg_b200.shims.install(force=True)
-    from kaolin.metrics.pointcloud import chamfer_distance as shim_chamfer
-    # Every step copies its own inputs from pinned host memory (one buffer per batch holding p1 then p2: a single H2D
-    # copy), runs the reference-facing call, and reads its own loss back before the next step is issued. The copy
-    # goes on the compute stream: the step is bound by the host side of autograd (bench_micro/e2e_profile.py), so a
-    # separate copy stream only adds host work.
+    # ---- end to end, headline: the host-buffer call of the C ABI (fpsg_chamfer_pipeline_*, fpsg_b200.ChamferPipeline): every
+    # step copies ITS inputs from pinned host memory (H2D, 1.57 MB), runs the fused loss step and reads its losses back
+    # (D2H); up to 3 steps are in flight, so the copies of step i+1 overlap the kernels of step i ----
     host = []
     for s_ in range(8):
-        h1, h2 = make_inputs(B, N, M, seed=777 + 1000 * rank + s_)
-        host.append(torch.cat([h1.reshape(-1), h2.reshape(-1)]).pin_memory())
+        h1, h2 = make_inputs(B, N, M, seed=777 + 1000 * rank + s_, pin=True)
+        host.append((h1, h2))
+    DEPTH = 3
+    pipe = fpsg_b200.ChamferPipeline(B, N, M, device=dev, depth=DEPTH)
+    e2e_steps = max(20, min(args.steps, 1000))
+    e2e_ring = torch.zeros(2, device=dev)
+
+    def e2e_loop(nsteps):
+        sub = 0
+        acc = 0.0
+        for i in range(nsteps):
+            while sub < nsteps and pipe.in_flight < DEPTH:
+                pipe.submit(*host[sub % len(host)])
+                sub += 1
+            s_, _loss, _gp1 = pipe.result()   # this step's loss sum, per-pair losses (host) and gradient (device)
+            acc += s_
+        return acc
+    e2e_loop(10)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(e2e_steps)
+    if world > 1:  # the logged global loss: one all-reduce of the accumulated sum closes the timed region
+        e2e_ring.zero_()
+        dist.all_reduce(e2e_ring)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    pipe.close()
+
+    # ---- end to end through the reference-facing Python call with autograd: kaolin shim chamfer_distance(p1, p2).sum()
+    # .backward(), one H2D copy per step from pinned memory, loss read back, stream synchronised every step ----
+    fpsg_b200.shims.install(force=True)
+    from kaolin.metrics.pointcloud import chamfer_distance as shim_chamfer
+    hcat = [torch.cat([h1.reshape(-1), h2.reshape(-1)]).pin_memory() for h1, h2 in host]
     n1 = B * N * 3
-    dbuf = torch.empty(host[0].numel(), device=dev)
+    dbuf = torch.empty(hcat[0].numel(), device=dev)
     p1_leaf = dbuf[:n1].view(B, N, 3).requires_grad_(True)   # the decoder output's stand-in: a leaf that wants a gradient
     p2_view = dbuf[n1:].view(B, M, 3)
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    cur = torch.cuda.current_stream(dev)
 
-    # N > 1: the global sum of the loss is a logged value only (the backward does not need it): as in the device-timed
-    # loop above, the per-step local sums are collected in a device-side ring and all-reduced KLOG steps per collective
-    # (one torch.distributed collective costs ~45 us of host time, the whole step ~160); ranks never wait for each other
-    # inside a step. What every step reads back and synchronises on is its own loss.
-    e2e_ring = [torch.zeros(KLOG, device=dev) for _ in range(2)]
-    e2e_work = [None, None]
-
-    def e2e_step(i):
+    def autograd_step(i):
         with torch.no_grad():
-            dbuf.copy_(host[i % len(host)], non_blocking=True)
+            dbuf.copy_(hcat[i % len(hcat)], non_blocking=True)
         p1_leaf.grad = None
         val = shim_chamfer(p1_leaf, p2_view).sum()
         val.backward()
         loss_host.copy_(val.detach(), non_blocking=True)
-        if world > 1:
-            kk, j = (i // KLOG) & 1, i % KLOG
-            if j == 0 and e2e_work[kk] is not None:
-                if not e2e_work[kk].is_completed():
-                    e2e_work[kk].wait()
-                e2e_work[kk] = None
-            e2e_ring[kk][j].copy_(val.detach())
-            if j == KLOG - 1:
-                e2e_work[kk] = dist.all_reduce(e2e_ring[kk], op=dist.ReduceOp.SUM, async_op=True)
-        cur.synchronize()  # the step's result (and its gradient) exist before the next step is issued
+        stream.synchronize()
         return float(loss_host)
-
-    e2e_steps = max(20, min(args.steps, 400))
+    ag_steps = max(20, min(args.steps, 300))
     for i in range(5):
-        e2e_step(i)
+        autograd_step(i)
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(5 + i)
-    for kk in (0, 1):
-        if e2e_work[kk] is not None:
-            e2e_work[kk].wait()
+    for i in range(ag_steps):
+        autograd_step(5 + i)
     barrier()
-    e2e_s = time.perf_counter() - t0
-
-    # ---- the same step through the C ABI itself with host buffers (what a native binding of the reference gets, without
-    # the autograd engine): H2D copy of the step's inputs from pinned memory, fused loss forward with the batch sum,
-    # backward to p1, D2H read of the scalar, stream synchronised -- every step. (Copying the next step's inputs on a
-    # second stream was tried and changes nothing: the step is host issue time + device time, not copy time.) ----
-    cabi_tot = torch.zeros(2, device=dev)
-    cabi_seg = (_lib.ChamferSegment * 1)()
-    cabi_seg[0].p1, cabi_seg[0].p2, cabi_seg[0].gp1, cabi_seg[0].gp2 = dbuf.data_ptr(), dbuf.data_ptr() + 4 * n1, None, None
-    cabi_seg[0].batch, cabi_seg[0].weight = B, 1.0
-    p1d, p2d = dbuf.data_ptr(), dbuf.data_ptr() + 4 * n1
-
-    def cabi_step(i):
-        dbuf.copy_(host[i % len(host)], non_blocking=True)
-        _lib.check(L.fpsg_chamfer_multi_loss_fwd(cabi_seg, 1, N, M, 1.0, 1.0, o[0], cabi_tot.data_ptr(), o[3], o[4], o[5], nbytes, sp))
-        _lib.check(L.fpsg_chamfer_loss_bwd(p1d, p2d, o[3], o[4], o[6], 1.0, 1.0, B, N, M, o[7], None, None, 0, sp))
-        loss_host.copy_(cabi_tot[0], non_blocking=True)
-        cur.synchronize()
-        return float(loss_host)
-
-    with torch.no_grad():
-        for i in range(5):
-            cabi_step(i)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            cabi_step(5 + i)
-        barrier()
-        cabi_s = time.perf_counter() - t0
+    ag_s = time.perf_counter() - t0
 
     # ---- reduce over ranks (max time) ----
     if world > 1:
-        t = torch.tensor([ms, e2e_s, cabi_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, ag_s, ms_nocoll], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, cabi_s = float(t[0]), float(t[1]), float(t[2])
+        ms, e2e_s, ag_s, ms_nocoll = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         pairs = world * B
         value = pairs * args.steps / (ms * 1e-3)
-        e2e_value = pairs * e2e_steps / e2e_s
         flops = 16.0 * B * N * M  # 2*N*M evaluations x 8 FLOP per pair
         achieved = flops / (sweep_us * 1e-6) / 1e12
+        step_us = ms / args.steps * 1e3
+        step_tf = flops / (step_us * 1e-6) / 1e12
         bwd_bytes = (36 * N + 24 * M) * B
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "global_pairs": pairs, "n_points": N, "m_points": M,
-                       "parallelism": f"batch-sharded x{world}" + (", scalar loss all-reduce (NCCL, 8 steps per collective)" if world > 1 else ""),
+                       "parallelism": f"batch-sharded x{world}", "collective": collective,
                        "l2": f"inputs rotate over {RING_SETS} distinct resident batches ({RING_SETS * B * (N + M) * 12 / 1e6:.0f} MB > 126 MB L2)",
-                       "launch": "C ABI via ctypes, stream-ordered, no CUDA graph"},
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps, "api": "kaolin.metrics.pointcloud.chamfer_distance(p1, p2).sum().backward() (fpsg_b200 shim); every step: one H2D copy of its inputs from pinned host memory, forward, backward, loss read back to the host, stream synchronised"},
-            "e2e_c_abi": {"value": pairs * e2e_steps / cabi_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": 4,
-                          "steps": e2e_steps,
-                          "api": "fpsg_chamfer_multi_loss_fwd + fpsg_chamfer_loss_bwd through ctypes (no autograd); every step: one H2D copy of "
-                                 "its inputs from pinned host memory, forward, backward, loss sum read back to the host, stream synchronised"},
+                       "launch": "C ABI via ctypes (fpsg_chamfer_multi_loss_fwd_bwd[_dist]: sweep + finish kernels), stream-ordered, no CUDA graph",
+                       "parity": "Chamfer oracle is parity-unpinned (Kaolin 0.9.0 absent): bit-exact vs the restated algorithm; kNN and input pipeline pinned"},
+            "e2e": {"value": pairs * e2e_steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": (2 + B) * 4,
+                    "steps": e2e_steps,
+                    "api": "fpsg_chamfer_pipeline_submit / _result (include/fpsg_b200.h; fpsg_b200.ChamferPipeline): every step copies its own inputs "
+                           "from pinned HOST memory, runs sweep + finish and reads its per-pair losses and their sum back to the host; depth 3, so the "
+                           "H2D copies of step i+1 overlap the kernels of step i; the gradient stays on the device as in the reference"},
+            "e2e_autograd": {"value": pairs * ag_steps / ag_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": 4,
+                             "steps": ag_steps,
+                             "api": "kaolin.metrics.pointcloud.chamfer_distance(p1, p2).sum().backward() (fpsg_b200 shim, torch.autograd); every step: one "
+                                    "H2D copy from pinned host memory, forward, backward, loss read back, stream synchronised (host-bound)"},
             "gpu_launches": kernels_per_step * args.steps,
-            "roofline": {"bound": "fp32_fma", "kernel": "chamfer_sweep_kernel<16,false>", "achieved": achieved, "peak": fp32_peak_tflops,
+            "roofline": {"bound": "fp32_fma", "kernel": "chamfer_sweep_kernel<16>", "achieved": achieved, "peak": fp32_peak_tflops,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": SWEEP_DRAM_TRAFFIC_BYTES,
+                         "traffic_source": SWEEP_DRAM_TRAFFIC_SOURCE,
                          "us_per_launch": sweep_us, "algorithmic_flop_per_launch": flops,
                          "peak_source": f"FFMA micro-kernel in this run (fpsg_probe_fp32_peak) at {probe_mhz:.0f} MHz; MEASURED_PEAKS.json has no FP32 row; "
                                         f"nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                          "how": "sweep kernel launched alone (fpsg_chamfer_sweep_only) over the same input ring, CUDA events on the launch stream"},
-            "roofline_bwd": {"bound": "hbm", "kernel": "chamfer_bwd_kernel", "achieved": bwd_bytes / (bwd_us * 1e-6) / 1e9, "peak": _hbm_peak(),
+            "roofline_step": {"bound": "fp32_fma", "what": "the whole fwd+bwd step (the north-star target: >= 0.60)", "achieved": step_tf,
+                              "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": step_tf / fp32_peak_tflops, "frac_of_nominal_74.4": step_tf / 74.4,
+                              "us_per_step": step_us, "algorithmic_flop_per_step": flops},
+            "roofline_bwd": {"bound": "hbm", "kernel": "chamfer_bwd_kernel (autograd path; the bench step runs the backward inside the finish kernel)",
+                             "achieved": bwd_bytes / (bwd_us * 1e-6) / 1e9, "peak": _hbm_peak(),
                              "unit": "GB/s", "us_per_launch": bwd_us, "algorithmic_bytes_per_launch": bwd_bytes,
                              "note": "3.9 MB working set is L2-resident: latency-, not bandwidth-bound (SURVEY.md 8d)"},
             "clocks": clocks,
             "secondary": secondary,
         }
+        if world > 1:
+            line["value_without_collective"] = pairs * args.steps / (ms_nocoll * 1e-3)
         line["roofline_bwd"]["frac"] = line["roofline_bwd"]["achieved"] / line["roofline_bwd"]["peak"]
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sec = cpu_formulation_pairs_per_s(sample_pairs=8, iters=3)

@@ -31,6 +31,16 @@ class ChamferSegment(ctypes.Structure):
                 ("batch", ctypes.c_int), ("weight", ctypes.c_float)]
 
 
+MAX_PEERS = 8
+PEER_RING = 4
+
+
+class PeerExchange(ctypes.Structure):
+    """``fpsg_peer_exchange_t`` of include/fpsg_b200.h."""
+    _fields_ = [("table", ctypes.c_void_p * MAX_PEERS), ("global_out", ctypes.c_void_p), ("rank", ctypes.c_int), ("world", ctypes.c_int),
+                ("seq", ctypes.c_uint), ("lag", ctypes.c_int)]
+
+
 def _declare(L: ctypes.CDLL) -> None:
     c_int, c_size_t, c_float, vp = ctypes.c_int, ctypes.c_size_t, ctypes.c_float, ctypes.c_void_p
     L.fpsg_abi_version.restype = c_int
@@ -58,6 +68,9 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_chamfer_loss_fwd_bwd.argtypes = [vp, vp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp]
     L.fpsg_chamfer_multi_loss_fwd_bwd.restype = c_int
     L.fpsg_chamfer_multi_loss_fwd_bwd.argtypes = [segp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, vp, c_size_t, vp]
+    L.fpsg_chamfer_multi_loss_fwd_bwd_dist.restype = c_int
+    L.fpsg_chamfer_multi_loss_fwd_bwd_dist.argtypes = [segp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, vp, c_size_t,
+                                                       ctypes.POINTER(PeerExchange), vp]
     szp, vpp = ctypes.POINTER(c_size_t), ctypes.POINTER(vp)
     L.fpsg_chamfer_pipeline_arena_bytes.restype = c_int
     L.fpsg_chamfer_pipeline_arena_bytes.argtypes = [c_int, c_int, c_int, c_int, szp, szp]

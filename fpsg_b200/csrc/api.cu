@@ -2,7 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 
-#include "common.cuh"
+#include "chamfer_plan.cuh"
 
 namespace fpsg {
 
@@ -32,6 +32,10 @@ struct ChamferPlan;
 int chamfer_fwd_bwd_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, float* loss,
                            float* totals, float w1, float w2, const float* gloss, const float* gtotal, bool multi, void* ws, size_t ws_bytes,
                            cudaStream_t stream, int mode);
+
+int chamfer_fwd_bwd_launch_px(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, float* loss,
+                              float* totals, float w1, float w2, const float* gloss, const float* gtotal, bool multi, void* ws, size_t ws_bytes,
+                              cudaStream_t stream, int mode, const PeerExchange* px);
 
 // host array of segments -> the table the kernels index; returns the total number of pairs or a negative error
 static int make_seg_table(const fpsg_chamfer_segment_t* segs, int nseg, SegTable* out) {
@@ -197,6 +201,31 @@ int fpsg_chamfer_multi_loss_fwd_bwd(const fpsg_chamfer_segment_t* segs_host, int
     if (!loss) return fail(FPSG_EINVAL, "chamfer_multi_loss_fwd_bwd: null loss");
     return chamfer_fwd_bwd_launch(t, B, N, M, nullptr, nullptr, idx1, idx2, loss, totals, w1, w2, nullptr, gtotal, true, ws, ws_bytes,
                                   static_cast<cudaStream_t>(stream), 0);
+}
+
+int fpsg_chamfer_multi_loss_fwd_bwd_dist(const fpsg_chamfer_segment_t* segs_host, int nseg, int N, int M, float w1, float w2, const float* gtotal,
+                                         float* loss, float* totals, int64_t* idx1, int64_t* idx2, void* ws, size_t ws_bytes,
+                                         const fpsg_peer_exchange_t* px_host, fpsg_stream_t stream) {
+    SegTable t;
+    const int B = make_seg_table(segs_host, nseg, &t);
+    if (B < 0) return B;
+    if (!totals || !loss) return fail(FPSG_EINVAL, "chamfer_multi_loss_fwd_bwd_dist: null loss / totals");
+    if (B == 0) return fail(FPSG_EINVAL, "chamfer_multi_loss_fwd_bwd_dist: every rank needs at least one pair");
+    PeerExchange px = {};
+    if (px_host) {
+        if (px_host->world < 1 || px_host->world > FPSG_MAX_PEERS || px_host->rank < 0 || px_host->rank >= px_host->world)
+            return fail(FPSG_EINVAL, "peer exchange: bad rank/world %d/%d", px_host->rank, px_host->world);
+        if (px_host->seq == 0 || (px_host->lag != 0 && px_host->lag != 1) || !px_host->global_out)
+            return fail(FPSG_EINVAL, "peer exchange: seq must start at 1, lag must be 0 or 1, global_out must not be null");
+        for (int r = 0; r < px_host->world; ++r) {
+            if (!px_host->table[r]) return fail(FPSG_EINVAL, "peer exchange: null table for rank %d", r);
+            px.table[r] = px_host->table[r];
+        }
+        px.global_out = px_host->global_out;
+        px.rank = px_host->rank, px.world = px_host->world, px.seq = px_host->seq, px.lag = px_host->lag;
+    }
+    return chamfer_fwd_bwd_launch_px(t, B, N, M, nullptr, nullptr, idx1, idx2, loss, totals, w1, w2, nullptr, gtotal, true, ws, ws_bytes,
+                                     static_cast<cudaStream_t>(stream), 0, px_host ? &px : nullptr);
 }
 
 size_t fpsg_chamfer_ws_diag_offset(int B, int N, int M) { return chamfer_diag_offset(B, N, M); }

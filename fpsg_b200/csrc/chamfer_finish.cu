@@ -58,6 +58,7 @@ struct FinishArgs {
     int N32, M32;    // cloud sizes rounded up to whole 32-point windows
     const unsigned* progress;   // the sweep CTAs' progress words (chamfer_plan.cuh)
     unsigned long long* trace;  // timeline stamps (tuning builds), else nullptr
+    PeerExchange px;            // multi-GPU scalar exchange in the batch-level epilogue (world == 0: none)
 };
 
 struct FinishSmem {
@@ -421,6 +422,7 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishClusterMax + 64, 2) 
                 total += (double)a.seg.weight[s] * (double)(float)acc;
             }
             if (lane == 0) a.totals[0] = (float)total;
+            peer_exchange(a.px, (float)total, lane);
         }
     }
     FPSG_TRACE(a.trace, 1, b * kFinishCluster + rank, 5);
@@ -431,7 +433,7 @@ bool chamfer_finish_supported(int N, int M) { return N <= kFinishMaxPoints && M 
 // Launches the finish kernel behind a sweep that used plan `pl` and workspace `ws`.
 int chamfer_finish_launch(const SegTable& seg, const ChamferPlan& pl, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
                           int64_t* idx2, float* loss, float* totals, float w1, float w2, const float* gloss, const float* gtotal, bool multi,
-                          void* ws, cudaStream_t stream) {
+                          void* ws, cudaStream_t stream, const PeerExchange* px) {
     bool want1 = false, want2 = false;
     for (int sg = 0; sg < seg.n; ++sg) {
         if (seg.b0[sg + 1] == seg.b0[sg]) continue;
@@ -462,6 +464,11 @@ int chamfer_finish_launch(const SegTable& seg, const ChamferPlan& pl, int B, int
     fa.M32 = (int)align_up((size_t)M, 32);
     fa.progress = reinterpret_cast<const unsigned*>(base + pl.progress_off);
     fa.trace = trace_buffer();
+    if (px) fa.px = *px;
+    else {
+        fa.px = PeerExchange{};
+        fa.px.world = 0;
+    }
     const int threads = fa.rpcN > fa.rpcM ? fa.rpcN : fa.rpcM;
     const FinishSmem L = finish_smem_layout(N, M, fa.rpcN, fa.rpcM, want2, threads / 32);
     const FinishSmemOff so{(unsigned)L.p2, (unsigned)L.p1, (unsigned)L.cnt1, (unsigned)L.bkt1, (unsigned)L.ovf1, (unsigned)L.cnt2, (unsigned)L.bkt2,
@@ -495,15 +502,16 @@ int chamfer_finish_launch(const SegTable& seg, const ChamferPlan& pl, int B, int
 int chamfer_prepare(const SegTable& seg, int B, int N, int M, void* ws, size_t ws_bytes, ChamferPlan* out);
 int chamfer_sweep_launch(const SegTable& seg, const ChamferPlan& pl, int B, int N, int M, void* ws, cudaStream_t stream);
 int chamfer_finalize_launch(const SegTable& seg, const ChamferPlan& pl, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
-                            int64_t* idx2, float* loss, float* totals, float w1, float w2, void* ws, cudaStream_t stream);
+                            int64_t* idx2, float* loss, float* totals, float w1, float w2, void* ws, cudaStream_t stream,
+                            const PeerExchange* px = nullptr);
 int chamfer_backward_launch(const SegTable& seg, const int64_t* idx1, const int64_t* idx2, const float* g1, const float* g2,
                             bool uniform, bool multi, const float* gtotal, float w1, float w2, int B, int N, int M, cudaStream_t stream);
 
 // One loss step with a known upstream gradient: sweep, then the fused finish kernel (clouds up to kFinishMaxPoints
 // points) or the finalize + backward kernels (larger clouds). mode (tuning builds): 1 forces the three-kernel chain.
-int chamfer_fwd_bwd_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, float* loss,
-                           float* totals, float w1, float w2, const float* gloss, const float* gtotal, bool multi, void* ws, size_t ws_bytes,
-                           cudaStream_t stream, int mode) {
+int chamfer_fwd_bwd_launch_px(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, float* loss,
+                              float* totals, float w1, float w2, const float* gloss, const float* gtotal, bool multi, void* ws, size_t ws_bytes,
+                              cudaStream_t stream, int mode, const PeerExchange* px) {
     if (B > 0 && (!idx1 || !idx2)) return fail(FPSG_EINVAL, "chamfer_fwd_bwd: null idx1/idx2");
     ChamferPlan pl;
     const int rc = chamfer_prepare(seg, B, N, M, ws, ws_bytes, &pl);
@@ -512,10 +520,18 @@ int chamfer_fwd_bwd_launch(const SegTable& seg, int B, int N, int M, float* dist
     if (rs != FPSG_OK) return rs;
     static const bool no_fuse = tune_env("FPSG_NO_FINISH") != nullptr;  // tuning build only
     if (chamfer_finish_supported(N, M) && mode != 1 && !no_fuse)
-        return chamfer_finish_launch(seg, pl, B, N, M, dist1, dist2, idx1, idx2, loss, totals, w1, w2, gloss, gtotal, multi, ws, stream);
-    const int rf = chamfer_finalize_launch(seg, pl, B, N, M, dist1, dist2, idx1, idx2, loss, totals, w1, w2, ws, stream);
+        return chamfer_finish_launch(seg, pl, B, N, M, dist1, dist2, idx1, idx2, loss, totals, w1, w2, gloss, gtotal, multi, ws, stream, px);
+    const int rf = chamfer_finalize_launch(seg, pl, B, N, M, dist1, dist2, idx1, idx2, loss, totals, w1, w2, ws, stream, px);
     if (rf != FPSG_OK) return rf;
     return chamfer_backward_launch(seg, idx1, idx2, gloss, gloss, true, multi, gtotal, w1, w2, B, N, M, stream);
+}
+
+
+int chamfer_fwd_bwd_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, float* loss,
+                           float* totals, float w1, float w2, const float* gloss, const float* gtotal, bool multi, void* ws, size_t ws_bytes,
+                           cudaStream_t stream, int mode) {
+    return chamfer_fwd_bwd_launch_px(seg, B, N, M, dist1, dist2, idx1, idx2, loss, totals, w1, w2, gloss, gtotal, multi, ws, ws_bytes, stream, mode,
+                                     nullptr);
 }
 
 }  // namespace fpsg

@@ -336,6 +336,7 @@ struct FinalizeArgs {
     float* totals;       // [1 + segments]: weighted total and per-segment sums of loss (nullptr: not wanted)
     int B;
     int stage;           // the cloud whose points are re-evaluated is staged in (dynamic) shared memory
+    PeerExchange px;     // multi-GPU scalar exchange in the batch-level epilogue (world == 0: none)
 };
 
 constexpr size_t kFinStageMaxBytes = 64 * 1024;    // clouds up to this size are staged
@@ -606,6 +607,7 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
                         total += (double)a.seg.weight[sg] * (double)(float)acc;
                     }
                     if (lane == 0) a.totals[0] = (float)total;
+                    peer_exchange(a.px, (float)total, lane);
                 }
             }
         }
@@ -668,12 +670,15 @@ int chamfer_sweep_launch(const SegTable& seg, const ChamferPlan& pl, int B, int 
 }
 
 int chamfer_finalize_launch(const SegTable& seg, const ChamferPlan& pl, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1,
-                            int64_t* idx2, float* loss, float* totals, float w1, float w2, void* ws, cudaStream_t stream) {
+                            int64_t* idx2, float* loss, float* totals, float w1, float w2, void* ws, cudaStream_t stream,
+                            const PeerExchange* px) {
     char* base = static_cast<char*>(ws);
     double* losspart = loss ? reinterpret_cast<double*>(base + pl.losspart_off) : nullptr;
     FinalizeArgs fa{seg, N, M, pl.R, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, reinterpret_cast<const float*>(base + pl.rowmin_off),
                     reinterpret_cast<const int*>(base + pl.rowsub_off), reinterpret_cast<const u64*>(base + pl.colpart_off),
-                    dist1, dist2, idx1, idx2, losspart, reinterpret_cast<unsigned*>(base + pl.counters_off), loss, w1, w2, pl.nrb, pl.ncb, totals, B, 0};
+                    dist1, dist2, idx1, idx2, losspart, reinterpret_cast<unsigned*>(base + pl.counters_off), loss, w1, w2, pl.nrb, pl.ncb, totals, B, 0, PeerExchange{}};
+    fa.px.world = 0;
+    if (px) fa.px = *px;
     if (pl.nrb + pl.ncb > 65535) return fail(FPSG_EINVAL, "chamfer: N + M too large for one call");
     const dim3 fgrid((unsigned)B, (unsigned)(pl.nrb + pl.ncb));
     size_t fin_smem = align_up((size_t)(N > M ? N : M), 32) * 12;  // whole 32-point windows
@@ -711,7 +716,7 @@ int chamfer_forward_launch(const SegTable& seg, int B, int N, int M, float* dist
     if (rc != FPSG_OK || B == 0) return rc;
     const int rs = chamfer_sweep_launch(seg, pl, B, N, M, ws, stream);
     if (rs != FPSG_OK || sweep_only) return rs;
-    return chamfer_finalize_launch(seg, pl, B, N, M, dist1, dist2, idx1, idx2, loss, totals, w1, w2, ws, stream);
+    return chamfer_finalize_launch(seg, pl, B, N, M, dist1, dist2, idx1, idx2, loss, totals, w1, w2, ws, stream, nullptr);
 }
 
 // Offset of the diagnostic counter (arg-min recoveries that found no candidate equal to the merged minimum) in a

@@ -56,7 +56,47 @@ struct SweepArgs {
     unsigned long long* trace;  // timeline stamps (tuning builds), else nullptr
 };
 
+// Scalar all-reduce through peer memory (multi-GPU, one process per GPU; include/fpsg_b200.h fpsg_peer_exchange_t): every
+// rank owns a small table of 64-bit words [kPeerRing][FPSG_MAX_PEERS] that all ranks can address (NVLink peer mapping).
+// The batch-level epilogue of a loss step publishes (seq << 32 | float bits of the local sum) into slot [seq % ring][rank]
+// of EVERY rank's table with one 8-byte store each -- value and flag travel in one word, so no fence is needed -- and then
+// sums, in rank order and in double, the `world` words of step seq - lag in its own table, polling until all have arrived.
+struct PeerExchange {
+    u64* table[FPSG_MAX_PEERS];  // table[p] = rank p's table as mapped into this process; nullptr entries beyond world
+    float* global_out;           // [kPeerRing] device: global_out[(seq - lag) % ring] = sum over ranks of that step
+    int rank, world;
+    unsigned seq;                // 1, 2, 3, ... one per step, identical on all ranks
+    int lag;                     // 0: wait for this step's values (a full all-reduce inside the step); 1: for the previous step's
+};
+constexpr int kPeerRing = FPSG_PEER_RING;
+
 #ifdef __CUDACC__
+// executed by one warp (the batch-level last arriver); `total` valid in lane 0
+__device__ __forceinline__ void peer_exchange(const PeerExchange& px, float total, int lane) {
+    if (px.world <= 0) return;
+    total = __shfl_sync(0xffffffffu, total, 0);
+    const u64 word = ((u64)px.seq << 32) | (u64)__float_as_uint(total);
+    if (lane < px.world) {
+        u64* dst = px.table[lane] + (px.seq % kPeerRing) * FPSG_MAX_PEERS + px.rank;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+    }
+    const unsigned want = px.seq - (unsigned)px.lag;
+    if (want == 0u) return;  // lag 1, first step: nothing to collect yet
+    float v = 0.f;
+    if (lane < px.world) {
+        const u64* src = px.table[px.rank] + (want % kPeerRing) * FPSG_MAX_PEERS + lane;
+        u64 got;
+        long long spins = 0;
+        do {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+        } while ((unsigned)(got >> 32) != want && ++spins < (1ll << 28));  // a dead peer must not hang the GPU for ever
+        v = (unsigned)(got >> 32) == want ? __uint_as_float((unsigned)got) : CUDART_NAN_F;
+    }
+    double acc = 0.0;
+    for (int r = 0; r < px.world; ++r) acc += (double)__shfl_sync(0xffffffffu, v, r);  // rank order: the same bits on every rank
+    if (lane == 0) px.global_out[want % kPeerRing] = (float)acc;
+}
+
 // which CTA owns unit u under the q/r partition
 __device__ __forceinline__ int cta_of_unit(int u, int q, int r) {
     const int cut = r * (q + 1);

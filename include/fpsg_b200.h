@@ -123,6 +123,33 @@ int fpsg_chamfer_multi_loss_fwd_bwd(const fpsg_chamfer_segment_t* segs_host, int
                                     float w2, const float* gtotal, float* loss, float* totals, int64_t* idx1,
                                     int64_t* idx2, void* ws, size_t ws_bytes, fpsg_stream_t stream);
 
+/* ---- Multi-GPU: the scalar loss all-reduce through NVLink peer memory ------------------------------------ */
+/* One process per GPU, the batch sharded over the ranks (pairs are independent); the only exchange of the path is the
+ * scalar the reference logs, sum_b loss[b] (src/models/few_shot.py:110,117,121). Instead of a collective launched from
+ * the host after the step, the loss kernel's own epilogue writes the rank's partial sum into every rank's table and
+ * sums what the other ranks wrote: `table[p]` is the device address, IN THIS PROCESS, of rank p's table of
+ * FPSG_PEER_RING * FPSG_MAX_PEERS 64-bit words (zero-initialised once; mapped through CUDA IPC / symmetric memory by
+ * the host code, see fpsg_b200/sharded.py). `seq` numbers the steps 1, 2, 3, ... identically on all ranks. With
+ * lag = 0 the epilogue waits for this step's values of all ranks -- a complete all-reduce inside the step; with
+ * lag = 1 it collects the PREVIOUS step's values, which have long arrived, so that no rank ever waits for another
+ * (the reduced value of the last step is then fetched with one more call with batch-less segments, or by lag = 0).
+ * global_out (FPSG_PEER_RING floats, device): global_out[(seq - lag) % FPSG_PEER_RING] = sum over the ranks, added
+ * in rank order (bit-identical on every rank). Pass px = NULL for a single-GPU step. */
+#define FPSG_MAX_PEERS 8
+#define FPSG_PEER_RING 4
+typedef struct fpsg_peer_exchange {
+    unsigned long long* table[FPSG_MAX_PEERS];
+    float* global_out;
+    int rank, world;
+    unsigned seq;
+    int lag;
+} fpsg_peer_exchange_t;
+/* fpsg_chamfer_multi_loss_fwd_bwd plus the exchange above in the same launch chain (no additional kernel). */
+int fpsg_chamfer_multi_loss_fwd_bwd_dist(const fpsg_chamfer_segment_t* segs_host, int nseg, int N, int M, float w1,
+                                         float w2, const float* gtotal, float* loss, float* totals, int64_t* idx1,
+                                         int64_t* idx2, void* ws, size_t ws_bytes, const fpsg_peer_exchange_t* px,
+                                         fpsg_stream_t stream);
+
 /* ---- Host-buffer streaming step ------------------------------------------------------------------------- */
 /* The reference's training loop around the loss (src/trainNetwork.py:141-148): `to_cuda(sample)`, `model.loss(sample)`,
  * `ttl_loss.backward()`, `.item()` -- per batch: H2D copy of p1 (B,N,3) and p2 (B,M,3) from HOST memory (pinned memory
