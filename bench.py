@@ -331,7 +331,10 @@ def main():
             from fpsg_b200.sharded import PeerScalarExchange
             try:
                 exchange = PeerScalarExchange(dev)
-                collective = "per step, inside the loss kernel's epilogue through NVLink peer memory (lag 0: every step waits for all ranks' values)"
+                collective = ("one all-reduce per step, done inside the loss kernel's epilogue through NVLink peer memory, software-pipelined "
+                              "(lag 1: step s publishes its sum and collects the sum of step s-1, a final flush collects the last one -- no rank ever "
+                              "waits for another); value_collective_in_step = the same with lag 0 (every step waits for all ranks' values of that step); "
+                              "value_without_collective = no exchange at all")
             except Exception as exc:  # symmetric memory unavailable: NCCL, amortised, as in round 1
                 print(f"[bench] peer exchange unavailable ({exc!r}); falling back to NCCL all-reduce, 8 steps per collective", file=sys.stderr)
                 ok = torch.zeros(1, device=dev)
@@ -380,13 +383,13 @@ def main():
 
     # One step = sweep + finish: per-pair losses, their sum over the local batch, the gradient w.r.t. p1 (the upstream
     # gradient of `.sum()` / `ttl_loss.backward()` is the constant 1), and for N > 1 the scalar exchange -- two kernels.
-    def step(i, with_collective=True):
-        if world == 1 or not with_collective:
+    def step(i, mode="lag1"):
+        if world == 1 or mode == "none":
             _lib.check(L.fpsg_chamfer_multi_loss_fwd_bwd(segs[i % RING_SETS], 1, N, M, 1.0, 1.0, None, out.data_ptr() + 8, out.data_ptr(), ip1, ip2,
                                                          ws.data_ptr(), nbytes, sp))
         elif exchange is not None:
             _lib.check(L.fpsg_chamfer_multi_loss_fwd_bwd_dist(segs[i % RING_SETS], 1, N, M, 1.0, 1.0, None, out.data_ptr() + 8, out.data_ptr(), ip1, ip2,
-                                                              ws.data_ptr(), nbytes, exchange.next(0), sp))
+                                                              ws.data_ptr(), nbytes, exchange.next(1 if mode == "lag1" else 0), sp))
         else:
             k, j = (i // KLOG) & 1, i % KLOG
             if j == 0 and pending[k] is not None:
@@ -405,13 +408,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed_steps(nsteps, with_collective=True):
+    def timed_steps(nsteps, mode="lag1"):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         tw0 = time.perf_counter()
         e0.record(stream)
         for i in range(nsteps):
-            step(args.warmup + i, with_collective)
+            step(args.warmup + i, mode)
+        if exchange is not None and mode == "lag1":
+            exchange.collect(exchange.seq, sp)  # the flush: the last step's sum
         e1.record(stream)
         for k in (0, 1):
             if pending[k] is not None:
@@ -425,11 +430,15 @@ def main():
         step(i)
     barrier()
     ms = timed_steps(args.steps)
-    ms_nocoll = None
-    if world > 1:  # the same loop without the collective
+    ms_nocoll = ms_lag0 = None
+    if world > 1:  # the same loop without the collective, and with the collective completed inside every step
+        nq = max(50, args.steps // 4)
         for i in range(10):
-            step(i, False)
-        ms_nocoll = timed_steps(max(50, args.steps // 4), False) / max(50, args.steps // 4) * args.steps
+            step(i, "none")
+        ms_nocoll = timed_steps(nq, "none") / nq * args.steps
+        for i in range(10):
+            step(i, "lag0")
+        ms_lag0 = timed_steps(nq, "lag0") / nq * args.steps
 
     # ---- dominant kernel alone (roofline), same ring, same stream ----
     def sweep(i):
@@ -516,8 +525,12 @@ def main():
         host.append((h1, h2))
     DEPTH = 3
     pipe = fpsg_b200.ChamferPipeline(B, N, M, device=dev, depth=DEPTH)
+    e2e_exchange = None
+    if exchange is not None:  # N > 1: every step of the pipeline takes part in the in-kernel scalar all-reduce (lag 1)
+        from fpsg_b200.sharded import PeerScalarExchange
+        e2e_exchange = PeerScalarExchange(dev)
+        pipe.set_exchange(e2e_exchange)
     e2e_steps = max(20, min(args.steps, 1000))
-    e2e_ring = torch.zeros(2, device=dev)
 
     def e2e_loop(nsteps):
         sub = 0
@@ -528,14 +541,13 @@ def main():
                 sub += 1
             s_, _loss, _gp1 = pipe.result()   # this step's loss sum, per-pair losses (host) and gradient (device)
             acc += s_
+            if e2e_exchange is not None and i >= 1 and (i & 63) == 0:
+                acc += 0.0 * pipe.previous_global_sum()  # the all-reduced loss of the previous step, as a logger would read it
         return acc
     e2e_loop(10)
     barrier()
     t0 = time.perf_counter()
     e2e_loop(e2e_steps)
-    if world > 1:  # the logged global loss: one all-reduce of the accumulated sum closes the timed region
-        e2e_ring.zero_()
-        dist.all_reduce(e2e_ring)
     barrier()
     e2e_s = time.perf_counter() - t0
     pipe.close()
@@ -572,9 +584,9 @@ def main():
 
     # ---- reduce over ranks (max time) ----
     if world > 1:
-        t = torch.tensor([ms, e2e_s, ag_s, ms_nocoll], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, ag_s, ms_nocoll, ms_lag0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, ag_s, ms_nocoll = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        ms, e2e_s, ag_s, ms_nocoll, ms_lag0 = (float(v) for v in t)
 
     if rank == 0:
         pairs = world * B
@@ -622,6 +634,7 @@ def main():
         }
         if world > 1:
             line["value_without_collective"] = pairs * args.steps / (ms_nocoll * 1e-3)
+            line["value_collective_in_step"] = pairs * args.steps / (ms_lag0 * 1e-3)
         line["roofline_bwd"]["frac"] = line["roofline_bwd"]["achieved"] / line["roofline_bwd"]["peak"]
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sec = cpu_formulation_pairs_per_s(sample_pairs=8, iters=3)

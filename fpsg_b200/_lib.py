@@ -71,6 +71,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_chamfer_multi_loss_fwd_bwd_dist.restype = c_int
     L.fpsg_chamfer_multi_loss_fwd_bwd_dist.argtypes = [segp, c_int, c_int, c_int, c_float, c_float, vp, vp, vp, vp, vp, vp, c_size_t,
                                                        ctypes.POINTER(PeerExchange), vp]
+    L.fpsg_peer_exchange_collect.restype = c_int
+    L.fpsg_peer_exchange_collect.argtypes = [ctypes.POINTER(PeerExchange), vp]
     szp, vpp = ctypes.POINTER(c_size_t), ctypes.POINTER(vp)
     L.fpsg_chamfer_pipeline_arena_bytes.restype = c_int
     L.fpsg_chamfer_pipeline_arena_bytes.argtypes = [c_int, c_int, c_int, c_int, szp, szp]
@@ -80,6 +82,10 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_chamfer_pipeline_submit.argtypes = [vp, vp, vp]
     L.fpsg_chamfer_pipeline_result.restype = c_int
     L.fpsg_chamfer_pipeline_result.argtypes = [vp, ctypes.POINTER(c_float), vp, vpp, vpp, vpp]
+    L.fpsg_chamfer_pipeline_set_exchange.restype = c_int
+    L.fpsg_chamfer_pipeline_set_exchange.argtypes = [vp, ctypes.POINTER(vp), c_int, c_int]
+    L.fpsg_chamfer_pipeline_previous_global_sum.restype = c_int
+    L.fpsg_chamfer_pipeline_previous_global_sum.argtypes = [vp, ctypes.POINTER(c_float)]
     L.fpsg_chamfer_pipeline_compute_stream.restype = vp
     L.fpsg_chamfer_pipeline_compute_stream.argtypes = [vp]
     L.fpsg_chamfer_pipeline_destroy.restype = c_int

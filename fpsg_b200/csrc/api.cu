@@ -94,6 +94,26 @@ __global__ void __launch_bounds__(512) fp32_peak_kernel(float* out, long long* c
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+__global__ void peer_collect_kernel(const PeerExchange px) {
+    cudaGridDependencySynchronize();
+    peer_collect(px, px.seq, (int)threadIdx.x);
+}
+
+static int convert_px(const fpsg_peer_exchange_t* h, PeerExchange* px) {
+    if (h->world < 1 || h->world > FPSG_MAX_PEERS || h->rank < 0 || h->rank >= h->world)
+        return fail(FPSG_EINVAL, "peer exchange: bad rank/world %d/%d", h->rank, h->world);
+    if (h->seq == 0 || (h->lag != 0 && h->lag != 1) || !h->global_out)
+        return fail(FPSG_EINVAL, "peer exchange: seq must start at 1, lag must be 0 or 1, global_out must not be null");
+    *px = PeerExchange{};
+    for (int r = 0; r < h->world; ++r) {
+        if (!h->table[r]) return fail(FPSG_EINVAL, "peer exchange: null table for rank %d", r);
+        px->table[r] = h->table[r];
+    }
+    px->global_out = h->global_out;
+    px->rank = h->rank, px->world = h->world, px->seq = h->seq, px->lag = h->lag;
+    return FPSG_OK;
+}
+
 }  // namespace fpsg
 
 using namespace fpsg;
@@ -213,19 +233,20 @@ int fpsg_chamfer_multi_loss_fwd_bwd_dist(const fpsg_chamfer_segment_t* segs_host
     if (B == 0) return fail(FPSG_EINVAL, "chamfer_multi_loss_fwd_bwd_dist: every rank needs at least one pair");
     PeerExchange px = {};
     if (px_host) {
-        if (px_host->world < 1 || px_host->world > FPSG_MAX_PEERS || px_host->rank < 0 || px_host->rank >= px_host->world)
-            return fail(FPSG_EINVAL, "peer exchange: bad rank/world %d/%d", px_host->rank, px_host->world);
-        if (px_host->seq == 0 || (px_host->lag != 0 && px_host->lag != 1) || !px_host->global_out)
-            return fail(FPSG_EINVAL, "peer exchange: seq must start at 1, lag must be 0 or 1, global_out must not be null");
-        for (int r = 0; r < px_host->world; ++r) {
-            if (!px_host->table[r]) return fail(FPSG_EINVAL, "peer exchange: null table for rank %d", r);
-            px.table[r] = px_host->table[r];
-        }
-        px.global_out = px_host->global_out;
-        px.rank = px_host->rank, px.world = px_host->world, px.seq = px_host->seq, px.lag = px_host->lag;
+        const int rc = convert_px(px_host, &px);
+        if (rc != FPSG_OK) return rc;
     }
     return chamfer_fwd_bwd_launch_px(t, B, N, M, nullptr, nullptr, idx1, idx2, loss, totals, w1, w2, nullptr, gtotal, true, ws, ws_bytes,
                                      static_cast<cudaStream_t>(stream), 0, px_host ? &px : nullptr);
+}
+
+int fpsg_peer_exchange_collect(const fpsg_peer_exchange_t* px_host, fpsg_stream_t stream) {
+    if (!px_host) return fail(FPSG_EINVAL, "peer_exchange_collect: null descriptor");
+    PeerExchange px;
+    const int rc = convert_px(px_host, &px);
+    if (rc != FPSG_OK) return rc;
+    FPSG_CUDA_OK(launch_pdl(peer_collect_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), px));
+    return FPSG_OK;
 }
 
 size_t fpsg_chamfer_ws_diag_offset(int B, int N, int M) { return chamfer_diag_offset(B, N, M); }

@@ -71,17 +71,9 @@ struct PeerExchange {
 constexpr int kPeerRing = FPSG_PEER_RING;
 
 #ifdef __CUDACC__
-// executed by one warp (the batch-level last arriver); `total` valid in lane 0
-__device__ __forceinline__ void peer_exchange(const PeerExchange& px, float total, int lane) {
-    if (px.world <= 0) return;
-    total = __shfl_sync(0xffffffffu, total, 0);
-    const u64 word = ((u64)px.seq << 32) | (u64)__float_as_uint(total);
-    if (lane < px.world) {
-        u64* dst = px.table[lane] + (px.seq % kPeerRing) * FPSG_MAX_PEERS + px.rank;
-        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
-    }
-    const unsigned want = px.seq - (unsigned)px.lag;
-    if (want == 0u) return;  // lag 1, first step: nothing to collect yet
+// one warp: sums, in rank order and in double, the `world` words of step `want` in this rank's own table, polling until
+// all have arrived, and writes global_out[want % ring]
+__device__ __forceinline__ void peer_collect(const PeerExchange& px, unsigned want, int lane) {
     float v = 0.f;
     if (lane < px.world) {
         const u64* src = px.table[px.rank] + (want % kPeerRing) * FPSG_MAX_PEERS + lane;
@@ -95,6 +87,20 @@ __device__ __forceinline__ void peer_exchange(const PeerExchange& px, float tota
     double acc = 0.0;
     for (int r = 0; r < px.world; ++r) acc += (double)__shfl_sync(0xffffffffu, v, r);  // rank order: the same bits on every rank
     if (lane == 0) px.global_out[want % kPeerRing] = (float)acc;
+}
+
+// executed by one warp (the batch-level last arriver); `total` valid in lane 0
+__device__ __forceinline__ void peer_exchange(const PeerExchange& px, float total, int lane) {
+    if (px.world <= 0) return;
+    total = __shfl_sync(0xffffffffu, total, 0);
+    const u64 word = ((u64)px.seq << 32) | (u64)__float_as_uint(total);
+    if (lane < px.world) {
+        u64* dst = px.table[lane] + (px.seq % kPeerRing) * FPSG_MAX_PEERS + px.rank;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+    }
+    const unsigned want = px.seq - (unsigned)px.lag;
+    if (want == 0u) return;  // lag 1, first step: nothing to collect yet
+    peer_collect(px, want, lane);
 }
 
 // which CTA owns unit u under the q/r partition

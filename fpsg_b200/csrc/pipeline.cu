@@ -14,14 +14,14 @@
 // A handle is used by one host thread at a time.
 #include <new>
 
-#include "common.cuh"
+#include "chamfer_plan.cuh"
 
 namespace fpsg {
 
 size_t chamfer_forward_workspace(int B, int N, int M);
-int chamfer_fwd_bwd_launch(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, float* loss,
-                           float* totals, float w1, float w2, const float* gloss, const float* gtotal, bool multi, void* ws, size_t ws_bytes,
-                           cudaStream_t stream, int mode);
+int chamfer_fwd_bwd_launch_px(const SegTable& seg, int B, int N, int M, float* dist1, float* dist2, int64_t* idx1, int64_t* idx2, float* loss,
+                              float* totals, float w1, float w2, const float* gloss, const float* gtotal, bool multi, void* ws, size_t ws_bytes,
+                              cudaStream_t stream, int mode, const PeerExchange* px);
 
 struct PipelineLayout {
     size_t in_off, gp1_off, idx_off, out_off, slot_bytes;  // per slot (device)
@@ -39,7 +39,7 @@ static PipelineLayout pipeline_layout(int B, int N, int M, int depth) {
     L.idx_off = off;
     off += align_up((size_t)B * (N + M) * sizeof(int64_t), 256);
     L.out_off = off;
-    L.out_bytes = align_up((2 + (size_t)B) * sizeof(float), 256);
+    L.out_bytes = align_up((2 + (size_t)B + FPSG_PEER_RING) * sizeof(float), 256);  // + the all-reduced sums (multi-GPU)
     off += L.out_bytes;
     L.slot_bytes = off;
     L.ws_off = L.slot_bytes * depth;
@@ -62,6 +62,7 @@ struct fpsg_chamfer_pipeline {
     cudaStream_t copy, compute;
     cudaEvent_t copied[8], done[8];
     long long head, tail;  // batches submitted / results taken
+    PeerExchange px;       // multi-GPU: the scalar exchange every step takes part in (world == 0: none), lag 1
 };
 
 extern "C" {
@@ -91,6 +92,7 @@ int fpsg_chamfer_pipeline_create(int B, int N, int M, float w1, float w2, int de
     p->dev = static_cast<char*>(device_arena);
     p->pinned = static_cast<char*>(pinned_host_arena);
     p->head = p->tail = 0;
+    p->px = PeerExchange{};
     p->copy = p->compute = nullptr;
     for (int i = 0; i < 8; ++i) p->copied[i] = p->done[i] = nullptr;
     cudaError_t e = cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking);
@@ -125,10 +127,15 @@ int fpsg_chamfer_pipeline_submit(fpsg_chamfer_pipeline_t* p, const float* p1_hos
     int64_t* idx1 = reinterpret_cast<int64_t*>(slot + p->L.idx_off);
     float* outrec = reinterpret_cast<float*>(slot + p->L.out_off);  // totals[2], then loss[B]
     SegTable t = single_segment(d1, d2, gp1, nullptr, p->B);
-    const int rc = chamfer_fwd_bwd_launch(t, p->B, p->N, p->M, nullptr, nullptr, idx1, idx1 + (size_t)p->B * p->N, outrec + 2, outrec, p->w1, p->w2,
-                                          nullptr, nullptr, true, p->dev + p->L.ws_off, p->L.ws_bytes, p->compute, 0);
+    PeerExchange px = p->px;
+    px.seq = (unsigned)(p->head + 1);
+    px.lag = 1;
+    px.global_out = outrec + 2 + p->B;  // this slot's copy of the ring: [(seq - 1) % ring] = the all-reduced sum of the previous batch
+    const int rc = chamfer_fwd_bwd_launch_px(t, p->B, p->N, p->M, nullptr, nullptr, idx1, idx1 + (size_t)p->B * p->N, outrec + 2, outrec, p->w1, p->w2,
+                                             nullptr, nullptr, true, p->dev + p->L.ws_off, p->L.ws_bytes, p->compute, 0, px.world > 0 ? &px : nullptr);
     if (rc != FPSG_OK) return rc;
-    FPSG_CUDA_OK(cudaMemcpyAsync(p->pinned + (size_t)s * p->L.out_bytes, outrec, (2 + (size_t)p->B) * sizeof(float), cudaMemcpyDeviceToHost, p->compute));
+    FPSG_CUDA_OK(cudaMemcpyAsync(p->pinned + (size_t)s * p->L.out_bytes, outrec, (2 + (size_t)p->B + FPSG_PEER_RING) * sizeof(float),
+                                 cudaMemcpyDeviceToHost, p->compute));
     FPSG_CUDA_OK(cudaEventRecord(p->done[s], p->compute));
     ++p->head;
     return FPSG_OK;
@@ -149,6 +156,29 @@ int fpsg_chamfer_pipeline_result(fpsg_chamfer_pipeline_t* p, float* loss_sum_hos
     if (idx1_device) *idx1_device = reinterpret_cast<const int64_t*>(slot + p->L.idx_off);
     if (idx2_device) *idx2_device = reinterpret_cast<const int64_t*>(slot + p->L.idx_off) + (size_t)p->B * p->N;
     ++p->tail;
+    return FPSG_OK;
+}
+
+int fpsg_chamfer_pipeline_set_exchange(fpsg_chamfer_pipeline_t* p, unsigned long long* const* tables, int rank, int world) {
+    if (!p) return fail(FPSG_EINVAL, "pipeline_set_exchange: null handle");
+    if (p->head != 0) return fail(FPSG_EINVAL, "pipeline_set_exchange: must be called before the first submit");
+    if (!tables || world < 1 || world > FPSG_MAX_PEERS || rank < 0 || rank >= world) return fail(FPSG_EINVAL, "pipeline_set_exchange: bad rank/world");
+    p->px = PeerExchange{};
+    for (int r = 0; r < world; ++r) {
+        if (!tables[r]) return fail(FPSG_EINVAL, "pipeline_set_exchange: null table for rank %d", r);
+        p->px.table[r] = tables[r];
+    }
+    p->px.rank = rank, p->px.world = world;
+    return FPSG_OK;
+}
+
+int fpsg_chamfer_pipeline_previous_global_sum(fpsg_chamfer_pipeline_t* p, float* global_sum_host) {
+    if (!p || !global_sum_host) return fail(FPSG_EINVAL, "pipeline_previous_global_sum: null argument");
+    if (p->px.world == 0 || p->tail < 2) return fail(FPSG_EINVAL, "pipeline_previous_global_sum: needs an exchange and two results taken");
+    // the batch whose result was taken last (number tail, 1-based) collected the sum of batch tail - 1
+    const int s = (int)((p->tail - 1) % p->depth);
+    const float* rec = reinterpret_cast<const float*>(p->pinned + (size_t)s * p->L.out_bytes);
+    *global_sum_host = rec[2 + p->B + (p->tail - 1) % FPSG_PEER_RING];
     return FPSG_OK;
 }
 

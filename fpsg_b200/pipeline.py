@@ -38,6 +38,19 @@ class ChamferPipeline:
         self._gp = ctypes.c_void_p()
         self._base = self._arena.data_ptr()
 
+    def set_exchange(self, exchange) -> None:
+        """Multi-GPU: every batch takes part in the in-kernel scalar all-reduce (``fpsg_b200.sharded.PeerScalarExchange``,
+        lag 1). All ranks must submit the same number of batches. Call before the first submit."""
+        tables = (ctypes.c_void_p * len(exchange.ptrs))(*exchange.ptrs)
+        _lib.check(_lib.lib().fpsg_chamfer_pipeline_set_exchange(self._h, tables, exchange.rank, exchange.world))
+        self._exchange = exchange
+
+    def previous_global_sum(self) -> float:
+        """After ``result()`` of batch n: the loss sum of batch n-1 over ALL ranks."""
+        v = ctypes.c_float()
+        _lib.check(_lib.lib().fpsg_chamfer_pipeline_previous_global_sum(self._h, ctypes.byref(v)))
+        return v.value
+
     def submit(self, p1_host: torch.Tensor, p2_host: torch.Tensor) -> None:
         for name, t, n in (("p1", p1_host, self.N), ("p2", p2_host, self.M)):
             if t.device.type != "cpu" or t.dtype != torch.float32 or tuple(t.shape) != (self.B, n, 3) or not t.is_contiguous():

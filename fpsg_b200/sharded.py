@@ -102,6 +102,15 @@ class PeerScalarExchange:
         px.rank, px.world, px.seq, px.lag = self.rank, self.world, self.seq, int(lag)
         return px
 
+    def collect(self, seq: int, stream: int) -> None:
+        """Enqueue the collection of step ``seq`` (the flush after the last step of a lag-1 sequence)."""
+        px = self._lib.PeerExchange()
+        for r in range(self.world):
+            px.table[r] = self.ptrs[r]
+        px.global_out = self.global_out.data_ptr()
+        px.rank, px.world, px.seq, px.lag = self.rank, self.world, int(seq), 0
+        self._lib.check(self._lib.lib().fpsg_peer_exchange_collect(px, stream))
+
     def global_sum(self, seq: int) -> torch.Tensor:
         """0-d view of the reduced value of step ``seq`` (valid once the step that collected it has run; the ring keeps
         the last ``PEER_RING`` steps)."""
@@ -143,6 +152,11 @@ class ShardedChamferStep:
                                                                    self.out.data_ptr(), ip, ip + 8 * self.B * self.N, self.ws.data_ptr(), self.nbytes,
                                                                    px, stream))
         return self.out[2:], self.out[0], self.gp1, px.seq
+
+    def flush(self) -> int:
+        """lag = 1: collect the last step's sum (nothing follows it that would). Returns its sequence number."""
+        self.exchange.collect(self.exchange.seq, torch.cuda.current_stream(self.device).cuda_stream)
+        return self.exchange.seq
 
     def global_sum(self, seq: int) -> torch.Tensor:
         return self.exchange.global_sum(seq)

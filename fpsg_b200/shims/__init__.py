@@ -4,8 +4,9 @@
   * registers ``kaolin``, ``kaolin.metrics`` and ``kaolin.metrics.pointcloud`` in ``sys.modules`` (unless a real
     Kaolin is importable and ``force`` is False), so that ``from kaolin.metrics.pointcloud import
     chamfer_distance`` (reference src/models/few_shot.py:13) resolves to the B200 implementation;
-  * if the reference's ``dgcnn.model`` module is (or later becomes) importable, rebinds its module-level ``knn``
-    to ``fpsg_b200.knn`` -- ``get_graph_feature`` looks ``knn`` up at call time (src/dgcnn/model.py:28).
+  * if the reference's ``dgcnn.model`` module is already imported, rebinds its module-level ``knn`` to
+    ``fpsg_b200.knn`` -- ``get_graph_feature`` looks ``knn`` up at call time (src/dgcnn/model.py:28). If the module is
+    imported later, call ``patch_dgcnn_knn()`` again.
 
 Alternatively put ``fpsg_b200/shims`` on ``PYTHONPATH``: the ``kaolin`` package in this directory is a regular
 importable package.
@@ -19,11 +20,16 @@ import sys
 
 def install(force: bool = False, patch_dgcnn: bool = True) -> None:
     have_real = False
-    if not force and "kaolin" not in sys.modules:
-        try:
-            have_real = importlib.util.find_spec("kaolin") is not None
-        except (ImportError, ValueError):
-            have_real = False
+    if not force:
+        loaded = sys.modules.get("kaolin")
+        if loaded is not None:
+            # something called kaolin is already imported: it is "real" unless it is this shim
+            have_real = not getattr(loaded, "__file__", "").startswith(__path__[0])
+        else:
+            try:
+                have_real = importlib.util.find_spec("kaolin") is not None
+            except (ImportError, ValueError):
+                have_real = False
     if force or not have_real:
         from .kaolin import metrics as _metrics  # noqa: F401
         from . import kaolin as _kaolin

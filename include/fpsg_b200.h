@@ -132,7 +132,7 @@ int fpsg_chamfer_multi_loss_fwd_bwd(const fpsg_chamfer_segment_t* segs_host, int
  * the host code, see fpsg_b200/sharded.py). `seq` numbers the steps 1, 2, 3, ... identically on all ranks. With
  * lag = 0 the epilogue waits for this step's values of all ranks -- a complete all-reduce inside the step; with
  * lag = 1 it collects the PREVIOUS step's values, which have long arrived, so that no rank ever waits for another
- * (the reduced value of the last step is then fetched with one more call with batch-less segments, or by lag = 0).
+ * (the reduced value of the last step is then fetched with fpsg_peer_exchange_collect).
  * global_out (FPSG_PEER_RING floats, device): global_out[(seq - lag) % FPSG_PEER_RING] = sum over the ranks, added
  * in rank order (bit-identical on every rank). Pass px = NULL for a single-GPU step. */
 #define FPSG_MAX_PEERS 8
@@ -149,6 +149,10 @@ int fpsg_chamfer_multi_loss_fwd_bwd_dist(const fpsg_chamfer_segment_t* segs_host
                                          float w2, const float* gtotal, float* loss, float* totals, int64_t* idx1,
                                          int64_t* idx2, void* ws, size_t ws_bytes, const fpsg_peer_exchange_t* px,
                                          fpsg_stream_t stream);
+
+/* Collects step px->seq without publishing anything (the flush after the last step of a lag = 1 sequence): a one-warp
+ * kernel that waits for the `world` values of that step and writes global_out[seq % FPSG_PEER_RING]. px->lag is ignored. */
+int fpsg_peer_exchange_collect(const fpsg_peer_exchange_t* px, fpsg_stream_t stream);
 
 /* ---- Host-buffer streaming step ------------------------------------------------------------------------- */
 /* The reference's training loop around the loss (src/trainNetwork.py:141-148): `to_cuda(sample)`, `model.loss(sample)`,
@@ -171,6 +175,11 @@ int fpsg_chamfer_pipeline_create(int B, int N, int M, float w1, float w2, int de
 int fpsg_chamfer_pipeline_submit(fpsg_chamfer_pipeline_t* p, const float* p1_host, const float* p2_host);
 int fpsg_chamfer_pipeline_result(fpsg_chamfer_pipeline_t* p, float* loss_sum_host, float* loss_host,
                                  const float** gp1_device, const int64_t** idx1_device, const int64_t** idx2_device);
+/* Multi-GPU: every batch of this pipeline takes part in the scalar exchange above with lag = 1 (seq = the batch's number,
+ * so all ranks must submit the same number of batches). tables[r] as in fpsg_peer_exchange_t; call before the first submit.
+ * fpsg_chamfer_pipeline_previous_global_sum: after the result of batch n was taken, the all-reduced loss sum of batch n-1. */
+int fpsg_chamfer_pipeline_set_exchange(fpsg_chamfer_pipeline_t* p, unsigned long long* const* tables, int rank, int world);
+int fpsg_chamfer_pipeline_previous_global_sum(fpsg_chamfer_pipeline_t* p, float* global_sum_host);
 /* The stream the kernels of the pipeline run on (to order a consumer of gp1 behind them without a host round trip). */
 fpsg_stream_t fpsg_chamfer_pipeline_compute_stream(fpsg_chamfer_pipeline_t* p);
 int fpsg_chamfer_pipeline_destroy(fpsg_chamfer_pipeline_t* p);
