@@ -265,6 +265,18 @@ def secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M)
                                 "multi_segment_us": _timed_us(torch, stream, dev, episode_one_call, 50)}
     del p1c2, p2c2, gp, ix, ws2
 
+    # ---- the evaluation metric beside the Chamfer distance (few_shot.py:168): Sinkhorn EMD of 32 pairs of 2048 points,
+    # geomloss' default schedule for diameter 2 (10 soft-min steps of four N x M sweeps each)
+    import fpsg_b200
+    from fpsg_b200.emd import epsilon_schedule
+    e1, e2 = make_inputs(32, N, M, seed=1234 + 6, device=dev)
+    sched = epsilon_schedule(2.0)
+    us = _timed_us(torch, stream, dev, lambda: fpsg_b200.emd_sinkhorn(e1, e2, eps_schedule=sched), 5, 2)
+    nexp = (len(sched) + 2) * 2.0 * 32 * (N * N + M * M + 2.0 * N * M) / 2
+    sec["emd_sinkhorn_B32_N2048"] = {"us_per_call": us, "pairs_per_s": 32 / us * 1e6, "softmin_steps": len(sched) + 2,
+                                     "exp_per_s": nexp / us * 1e6, "note": "evaluation-only metric, parity unpinned (geomloss absent)"}
+    del e1, e2
+
     # ---- c4: large clouds, B=64, N=M in {4096, 8192, 16384}
     for n4 in (4096, 8192, 16384):
         B4 = 64

@@ -129,6 +129,80 @@ __global__ void __launch_bounds__(128, (MODE >= 2 ? 3 : 4)) loop_kernel(const fl
     if (tid == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// MODE 4/5: expanded-form FILTER loop (round 2): e = fma(a'x,bx, fma(a'y,by, fma(a'z,bz, bb))) + aa with a' = -2a: 3 FFMA + 1 FADD
+// per evaluation; row direction min3 into a piece minimum; column direction thread minimum, CREDUX, and a ballot of the lanes
+// within a tolerance of the warp minimum (one FADD + FSETP per column). RR rows per thread (16 or 8).
+template <int RR, int CTAS>
+__global__ void __launch_bounds__(128, CTAS) filter_kernel(const float* __restrict__ rows, const float* __restrict__ cols, float* out, long long* cycles, float tol) {
+    __shared__ __align__(16) float tile[TILE * 4];  // (x, y, z, bb) per column
+    __shared__ u64 res[4][TILE];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int i = tid; i < TILE; i += 128) {
+        const float x = cols[3 * i], y = cols[3 * i + 1], z = cols[3 * i + 2];
+        tile[4 * i] = x; tile[4 * i + 1] = y; tile[4 * i + 2] = z; tile[4 * i + 3] = x * x + y * y + z * z;
+    }
+    float ax[RR], ay[RR], az[RR], aa[RR], pm[RR];
+#pragma unroll
+    for (int k = 0; k < RR; ++k) {
+        const float x = rows[(tid * RR + k) * 3], y = rows[(tid * RR + k) * 3 + 1], z = rows[(tid * RR + k) * 3 + 2];
+        ax[k] = -2.f * x; ay[k] = -2.f * y; az[k] = -2.f * z; aa[k] = x * x + y * y + z * z; pm[k] = CUDART_INF_F;
+    }
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int s = 0; s < STEPS; ++s) {
+        const int step = s & 15;
+        const float4 q0 = *reinterpret_cast<const float4*>(tile + 16 * step);
+        const float4 q1 = *reinterpret_cast<const float4*>(tile + 16 * step + 4);
+        const float4 q2 = *reinterpret_cast<const float4*>(tile + 16 * step + 8);
+        const float4 q3 = *reinterpret_cast<const float4*>(tile + 16 * step + 12);
+        float c0m = CUDART_INF_F, c1m = CUDART_INF_F, c2m = CUDART_INF_F, c3m = CUDART_INF_F;
+#pragma unroll
+        for (int k = 0; k < RR; k += 2) {
+            const float a0 = __fadd_rn(__fmaf_rn(ax[k], q0.x, __fmaf_rn(ay[k], q0.y, __fmaf_rn(az[k], q0.z, q0.w))), aa[k]);
+            const float a1 = __fadd_rn(__fmaf_rn(ax[k], q1.x, __fmaf_rn(ay[k], q1.y, __fmaf_rn(az[k], q1.z, q1.w))), aa[k]);
+            const float a2 = __fadd_rn(__fmaf_rn(ax[k], q2.x, __fmaf_rn(ay[k], q2.y, __fmaf_rn(az[k], q2.z, q2.w))), aa[k]);
+            const float a3 = __fadd_rn(__fmaf_rn(ax[k], q3.x, __fmaf_rn(ay[k], q3.y, __fmaf_rn(az[k], q3.z, q3.w))), aa[k]);
+            const float b0 = __fadd_rn(__fmaf_rn(ax[k + 1], q0.x, __fmaf_rn(ay[k + 1], q0.y, __fmaf_rn(az[k + 1], q0.z, q0.w))), aa[k + 1]);
+            const float b1 = __fadd_rn(__fmaf_rn(ax[k + 1], q1.x, __fmaf_rn(ay[k + 1], q1.y, __fmaf_rn(az[k + 1], q1.z, q1.w))), aa[k + 1]);
+            const float b2 = __fadd_rn(__fmaf_rn(ax[k + 1], q2.x, __fmaf_rn(ay[k + 1], q2.y, __fmaf_rn(az[k + 1], q2.z, q2.w))), aa[k + 1]);
+            const float b3 = __fadd_rn(__fmaf_rn(ax[k + 1], q3.x, __fmaf_rn(ay[k + 1], q3.y, __fmaf_rn(az[k + 1], q3.z, q3.w))), aa[k + 1]);
+            pm[k] = min3(min3(pm[k], a0, a1), a2, a3);
+            pm[k + 1] = min3(min3(pm[k + 1], b0, b1), b2, b3);
+            c0m = min3(c0m, a0, b0); c1m = min3(c1m, a1, b1); c2m = min3(c2m, a2, b2); c3m = min3(c3m, a3, b3);
+        }
+        const float m0 = warp_min_f32(c0m), m1 = warp_min_f32(c1m), m2 = warp_min_f32(c2m), m3 = warp_min_f32(c3m);
+        const unsigned h0 = __ballot_sync(0xffffffffu, c0m <= m0 + tol), h1 = __ballot_sync(0xffffffffu, c1m <= m1 + tol);
+        const unsigned h2 = __ballot_sync(0xffffffffu, c2m <= m2 + tol), h3 = __ballot_sync(0xffffffffu, c3m <= m3 + tol);
+        if (lane == 0) {
+            res[w][4 * step + 0] = ((u64)__float_as_uint(m0) << 32) | h0; res[w][4 * step + 1] = ((u64)__float_as_uint(m1) << 32) | h1;
+            res[w][4 * step + 2] = ((u64)__float_as_uint(m2) << 32) | h2; res[w][4 * step + 3] = ((u64)__float_as_uint(m3) << 32) | h3;
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < RR; ++k) s += pm[k];
+    __syncthreads();
+    s += (float)(res[w][lane] & 0xff);
+    out[blockIdx.x * 128 + tid] = s;
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int RR, int CTAS>
+void run_filter(const char* name, int sms, const float* rows, const float* cols, float* out, long long* cyc) {
+    const int grid = sms * CTAS;
+    filter_kernel<RR, CTAS><<<grid, 128>>>(rows, cols, out, cyc, 1e-6f);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    filter_kernel<RR, CTAS><<<grid, 128>>>(rows, cols, out, cyc, 1e-6f);
+    CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double evals = (double)grid * 128 * RR * 4 * STEPS;
+    printf("{\"loop\": \"%s\", \"rows_per_thread\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, \"tera_evals_per_s\": %.3f}\n", name, RR, CTAS, ms, evals / (ms * 1e-3) / 1e12);
+}
+
 template <int MODE>
 void run(const char* name, int ctas_per_sm, int sms, const float* rows, const float* cols, float* out, long long* cyc) {
     const int grid = sms * ctas_per_sm;
@@ -164,5 +238,19 @@ int main() {
         run<1>("scalar+colreduce", c, sms, rows, cols, out, cyc);
         if (c <= 3) { run<2>("packed", c, sms, rows, cols, out, cyc); run<3>("packed+colreduce", c, sms, rows, cols, out, cyc); }
     }
+    // reference point in the same units: the shipped loop at 4 CTAs/SM
+    {
+        const int grid = sms * 4;
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        loop_kernel<1><<<grid, 128>>>(rows, cols, out, cyc); CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0)); loop_kernel<1><<<grid, 128>>>(rows, cols, out, cyc); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf("{\"loop\": \"exact (shipped)\", \"rows_per_thread\": 16, \"ctas_per_sm\": 4, \"ms\": %.4f, \"tera_evals_per_s\": %.3f}\n", ms, (double)grid * 128 * R * 4 * STEPS / (ms * 1e-3) / 1e12);
+    }
+    run_filter<16, 3>("filter", sms, rows, cols, out, cyc);
+    run_filter<16, 4>("filter", sms, rows, cols, out, cyc);
+    run_filter<8, 4>("filter", sms, rows, cols, out, cyc);
+    run_filter<8, 5>("filter", sms, rows, cols, out, cyc);
+    run_filter<8, 6>("filter", sms, rows, cols, out, cyc);
     return 0;
 }

@@ -6,11 +6,12 @@ forward/backward and the DGCNN kNN graph, behind the reference's own call surfac
 """
 from .chamfer import (chamfer_distance, chamfer_loss, chamfer_loss_and_grad, chamfer_loss_multi, chamfer_loss_multi_and_grad,
                       sided_distance)
+from .emd import emd_sinkhorn
 from .graph_feature import get_graph_feature
 from .knn import knn
 from .pipeline import ChamferPipeline
 from .pointcloud_io import normalize_point_clouds, ply_reader
 
-__all__ = ["chamfer_distance", "chamfer_loss", "chamfer_loss_and_grad", "chamfer_loss_multi", "chamfer_loss_multi_and_grad", "sided_distance", "ChamferPipeline", "knn", "get_graph_feature", "ply_reader",
+__all__ = ["chamfer_distance", "chamfer_loss", "chamfer_loss_and_grad", "chamfer_loss_multi", "chamfer_loss_multi_and_grad", "sided_distance", "emd_sinkhorn", "ChamferPipeline", "knn", "get_graph_feature", "ply_reader",
            "normalize_point_clouds"]
 __version__ = "0.1.0"

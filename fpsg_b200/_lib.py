@@ -92,6 +92,10 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_chamfer_pipeline_destroy.argtypes = [vp]
     L.fpsg_chamfer_ws_diag_offset.restype = c_size_t
     L.fpsg_chamfer_ws_diag_offset.argtypes = [c_int, c_int, c_int]
+    L.fpsg_emd_sinkhorn_workspace_bytes.restype = c_size_t
+    L.fpsg_emd_sinkhorn_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    L.fpsg_emd_sinkhorn_fwd.restype = c_int
+    L.fpsg_emd_sinkhorn_fwd.argtypes = [vp, vp, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_int, vp, vp, vp, vp, c_size_t, vp]
     L.fpsg_knn_workspace_bytes.restype = c_size_t
     L.fpsg_knn_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     L.fpsg_knn_fwd.restype = c_int

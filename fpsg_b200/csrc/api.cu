@@ -65,6 +65,9 @@ int edge_feature_backward_launch(const float* g, const int64_t* idx, int B, int 
                                  cudaStream_t stream);
 int normalize_clouds_launch(const float* in, int B, int N, float* out, cudaStream_t stream);
 int ply_read_ascii(const char* path, int max_points, float* xyz, int* n_points);
+size_t emd_workspace(int B, int N, int M);
+int emd_forward_launch(const float* p1, const float* p2, int B, int N, int M, const float* eps_host, int n_eps, int debias, float* out, float* f_out,
+                       float* g_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t knn_workspace(int B, int C, int N, int k);
 int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t stream);
 
@@ -250,6 +253,13 @@ int fpsg_peer_exchange_collect(const fpsg_peer_exchange_t* px_host, fpsg_stream_
 }
 
 size_t fpsg_chamfer_ws_diag_offset(int B, int N, int M) { return chamfer_diag_offset(B, N, M); }
+
+size_t fpsg_emd_sinkhorn_workspace_bytes(int B, int N, int M) { return emd_workspace(B, N, M); }
+
+int fpsg_emd_sinkhorn_fwd(const float* p1, const float* p2, int B, int N, int M, const float* eps_schedule_host, int n_eps, int debias, float* out,
+                          float* f_out, float* g_out, void* ws, size_t ws_bytes, fpsg_stream_t stream) {
+    return emd_forward_launch(p1, p2, B, N, M, eps_schedule_host, n_eps, debias, out, f_out, g_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
 
 size_t fpsg_knn_workspace_bytes(int B, int C, int N, int k) { return knn_workspace(B, C, N, k); }
 

@@ -41,6 +41,25 @@ def install(force: bool = False, patch_dgcnn: bool = True) -> None:
         patch_dgcnn_knn()
 
 
+def install_neuralnet_pytorch(force: bool = False) -> bool:
+    """Registers the ``neuralnet_pytorch`` shim (``metrics.emd_loss`` with ``sinkhorn=True`` -> ``fpsg_b200.emd_sinkhorn``;
+    reference src/models/utils.py:9-13) unless the real package is importable and ``force`` is False. Returns True if the
+    shim is in place. Kept separate from ``install()``: the metric is evaluation-only and parity-unpinned."""
+    if not force:
+        if "neuralnet_pytorch" in sys.modules:
+            return getattr(sys.modules["neuralnet_pytorch"], "__file__", "").startswith(__path__[0])
+        try:
+            if importlib.util.find_spec("neuralnet_pytorch") is not None:
+                return False
+        except (ImportError, ValueError):
+            pass
+    from . import neuralnet_pytorch as _nnt
+    from .neuralnet_pytorch import metrics as _m
+    sys.modules["neuralnet_pytorch"] = _nnt
+    sys.modules["neuralnet_pytorch.metrics"] = _m
+    return True
+
+
 def patch_dgcnn_knn(module=None, graph_feature: bool = False) -> bool:
     """Rebinds ``knn`` in the reference's dgcnn.model (already imported, or given). Returns True if patched.
     With ``graph_feature=True`` the module's ``get_graph_feature`` (src/dgcnn/model.py:23-42, looked up as a module

@@ -5,7 +5,7 @@ The sources are imported from baseline/_ref/src, a git-ignored copy of /root/ref
 `__graft_entry__.build()` (the reference tree itself does not exist on the GPU box). The reference cannot run through its
 CLIs (argparse typo, missing third-party packages), so the harness imports the modules and drives
 `DGCNNfeat.forward` and `ImgPCProtoNet.loss` directly; the packages that are absent from the image and lie OFF the hot path
-(imageio, pymesh, neuralnet_pytorch, matplotlib) are stubbed, the VGG image encoder (needs a weight download) is replaced
+(imageio, pymesh, matplotlib) are stubbed, `neuralnet_pytorch.metrics.emd_loss` resolves to the Sinkhorn-EMD shim, the VGG image encoder (needs a weight download) is replaced
 by a small stand-in. Everything on the path -- `knn`, `get_graph_feature`, `DGCNNfeat`, `PCEncoder`, `PCDecoder`,
 `ImgPCProtoNet` and its `chamfer_distance(...).sum()` calls -- is the reference's code."""
 import importlib
@@ -37,20 +37,16 @@ def reference_modules():
     for n in saved:
         del sys.modules[n]
     stubs = {}
-    for name in ("imageio", "pymesh", "neuralnet_pytorch", "neuralnet_pytorch.metrics", "matplotlib", "matplotlib.pyplot"):
+    for name in ("imageio", "pymesh", "matplotlib", "matplotlib.pyplot"):
         m = types.ModuleType(name)
         stubs[name] = m
-    stubs["neuralnet_pytorch"].metrics = stubs["neuralnet_pytorch.metrics"]
-
-    def _no_emd(*a, **k):
-        raise RuntimeError("neuralnet_pytorch.metrics.emd_loss is not available in this image (eval-only metric, off the path)")
-    stubs["neuralnet_pytorch.metrics"].emd_loss = _no_emd
     stubs["matplotlib"].use = lambda *a, **k: None
     stubs["matplotlib"].pyplot = stubs["matplotlib.pyplot"]
     sys.modules.update(stubs)
     sys.path.insert(0, REF_SRC)
     import fpsg_b200.shims
     fpsg_b200.shims.install(force=True, patch_dgcnn=False)   # kaolin.metrics.pointcloud -> fpsg_b200 (few_shot.py:13)
+    fpsg_b200.shims.install_neuralnet_pytorch(force=True)    # neuralnet_pytorch.metrics.emd_loss -> fpsg_b200 (models/utils.py:9)
     try:
         dg = importlib.import_module("dgcnn.model")
         assert os.path.realpath(dg.__file__).startswith(os.path.realpath(REF_SRC))
@@ -58,7 +54,7 @@ def reference_modules():
     finally:
         sys.path.remove(REF_SRC)
         for n in list(sys.modules):
-            if n.split(".")[0] in _REF_PACKAGES or n in stubs:
+            if n.split(".")[0] in _REF_PACKAGES or n in stubs or n.split(".")[0] == "neuralnet_pytorch":
                 del sys.modules[n]
         sys.modules.update(saved)
 
@@ -202,3 +198,38 @@ def test_reference_protonet_loss_backward_through_the_shim(reference_modules, co
     assert abs(float(ans["ttl_loss"]) - (sums[0] + 0.5 * sums[1])) <= 1e-5 * abs(sums[0] + 0.5 * sums[1])
     grads = [p.grad for p in model.pc_decoder.parameters() if p.grad is not None]
     assert grads and all(torch.isfinite(gr).all() for gr in grads) and any(float(gr.abs().max()) > 0 for gr in grads)
+
+
+def test_reference_eval_reconstruction_cd_and_emd(reference_modules):
+    """`ImgPCProtoNet._return_reconstruction` (src/models/few_shot.py:131-176, the evaluation path of
+    src/evaluate_Network.py:110, under no_grad): `self.pc_metric(syn_pc, ref).sum()` (:167) and
+    `emd_wrapper(syn_pc, ref).sum()` (:168) both run on the B200 kernels through the two shims."""
+    import fpsg_b200.shims
+    from fpsg_b200.emd import epsilon_schedule, max_diameter
+    from oracle import cpu_oracle as O
+    from oracle import emd_oracle as E
+    fs = importlib.import_module("models.few_shot")
+    pcn = importlib.import_module("models.point_cloud_net")
+    conf = types.SimpleNamespace(device="cuda", num_nodes=4, num_clusters=4, ori_dim=2, raw_dim=3, bottleneck_size=1536,
+                                 template_type="SQUARE", activation="relu")
+    torch.manual_seed(3)
+    model = fs.ImgPCProtoNet(_TinyImageEncoder(), pcn.PCEncoder("pointnet"), pcn.PCDecoder(conf, num_pts=2048), metric="cd").cuda().eval()
+    n_s, n_q = 3, 2
+    g = torch.Generator().manual_seed(4)
+    sample = {"xs": torch.randn(1, n_s, 3, 16, 16, generator=g).cuda(), "xq": torch.randn(1, n_q, 3, 16, 16, generator=g).cuda(),
+              "xad": torch.randn(1, n_s, 3, 16, 16, generator=g).cuda(),
+              "pcs": _cloud(n_s, 2048, 6)[None].cuda(), "pcq": _cloud(n_q, 2048, 7)[None].cuda(), "pcad": _cloud(n_s, 2048, 8)[None].cuda()}
+    seen = []
+    h = model.pc_decoder.register_forward_hook(lambda _m, _i, out: seen.append(out.detach().clone()))
+    with torch.no_grad():
+        ans = model._return_reconstruction(sample)
+    h.remove()
+    syn, ref = seen[0], sample["pcq"][0]
+    oloss = O.chamfer_fwd(syn.cpu().numpy(), ref.cpu().numpy())[4]
+    assert abs(float(ans["cd_loss"]) - float(oloss.astype(np.float64).sum())) <= 1e-5 * float(oloss.sum())
+    sched = epsilon_schedule(max_diameter(syn, ref))
+    want = E.emd_sinkhorn(syn.cpu().numpy()[:, ::4], ref.cpu().numpy()[:, ::4], sched)  # (sub-sampled: the float64 oracle is dense)
+    import fpsg_b200
+    sub = fpsg_b200.emd_sinkhorn(syn[:, ::4].contiguous(), ref[:, ::4].contiguous(), eps_schedule=sched)
+    assert np.abs(sub.cpu().numpy() - want).max() <= 1e-4 * np.abs(want).max() + 2e-6
+    assert torch.isfinite(ans["emd_loss"]) and float(ans["emd_loss"]) > 0
