@@ -105,8 +105,8 @@ __global__ void peer_collect_kernel(const PeerExchange px) {
 static int convert_px(const fpsg_peer_exchange_t* h, PeerExchange* px) {
     if (h->world < 1 || h->world > FPSG_MAX_PEERS || h->rank < 0 || h->rank >= h->world)
         return fail(FPSG_EINVAL, "peer exchange: bad rank/world %d/%d", h->rank, h->world);
-    if (h->seq == 0 || (h->lag != 0 && h->lag != 1) || !h->global_out)
-        return fail(FPSG_EINVAL, "peer exchange: seq must start at 1, lag must be 0 or 1, global_out must not be null");
+    if (h->seq == 0 || h->lag < 0 || h->lag > FPSG_PEER_RING / 4 || !h->global_out)
+        return fail(FPSG_EINVAL, "peer exchange: seq must start at 1, lag must be in [0, %d], global_out must not be null", FPSG_PEER_RING / 4);
     *px = PeerExchange{};
     for (int r = 0; r < h->world; ++r) {
         if (!h->table[r]) return fail(FPSG_EINVAL, "peer exchange: null table for rank %d", r);

@@ -66,7 +66,7 @@ struct PeerExchange {
     float* global_out;           // [kPeerRing] device: global_out[(seq - lag) % ring] = sum over ranks of that step
     int rank, world;
     unsigned seq;                // 1, 2, 3, ... one per step, identical on all ranks
-    int lag;                     // 0: wait for this step's values (a full all-reduce inside the step); 1: for the previous step's
+    int lag;                     // 0: wait for this step's values (a full all-reduce inside the step); L >= 1: for those of step seq - L
 };
 constexpr int kPeerRing = FPSG_PEER_RING;
 
@@ -98,8 +98,8 @@ __device__ __forceinline__ void peer_exchange(const PeerExchange& px, float tota
         u64* dst = px.table[lane] + (px.seq % kPeerRing) * FPSG_MAX_PEERS + px.rank;
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
     }
+    if (px.seq <= (unsigned)px.lag) return;  // the first `lag` steps: nothing to collect yet
     const unsigned want = px.seq - (unsigned)px.lag;
-    if (want == 0u) return;  // lag 1, first step: nothing to collect yet
     peer_collect(px, want, lane);
 }
 

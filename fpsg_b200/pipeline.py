@@ -1,7 +1,8 @@
 """Host-buffer streaming Chamfer step (include/fpsg_b200.h, fpsg_chamfer_pipeline_*): the shape of the reference's
 training loop around the loss -- ``to_cuda(sample)``, ``model.loss(sample)``, ``ttl_loss.backward()``, ``.item()``
 (reference src/trainNetwork.py:141-148) -- with the H2D copies of the next batch overlapped with the kernels of
-the current one. The runtime (streams, events, slots) is native code in libfpsg_b200.so; this class owns the two arenas
+the current one, and (every slot being a lane with its own stream and workspace) the latency-bound tail of a batch
+overlapped with the distance sweep of the next. The runtime (streams, events, slots) is native code in libfpsg_b200.so; this class owns the two arenas
 (a device tensor and a pinned host tensor) and turns results into tensors."""
 from __future__ import annotations
 
@@ -40,13 +41,13 @@ class ChamferPipeline:
 
     def set_exchange(self, exchange) -> None:
         """Multi-GPU: every batch takes part in the in-kernel scalar all-reduce (``fpsg_b200.sharded.PeerScalarExchange``,
-        lag 1). All ranks must submit the same number of batches. Call before the first submit."""
+        lag = depth <= 4). All ranks must submit the same number of batches. Call before the first submit."""
         tables = (ctypes.c_void_p * len(exchange.ptrs))(*exchange.ptrs)
         _lib.check(_lib.lib().fpsg_chamfer_pipeline_set_exchange(self._h, tables, exchange.rank, exchange.world))
         self._exchange = exchange
 
     def previous_global_sum(self) -> float:
-        """After ``result()`` of batch n: the loss sum of batch n-1 over ALL ranks."""
+        """After ``result()`` of batch n (n > depth): the loss sum of batch n - depth over ALL ranks."""
         v = ctypes.c_float()
         _lib.check(_lib.lib().fpsg_chamfer_pipeline_previous_global_sum(self._h, ctypes.byref(v)))
         return v.value

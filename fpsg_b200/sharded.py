@@ -123,7 +123,7 @@ class ShardedChamferStep:
     ``step = ShardedChamferStep(B_local, N, M, device)``; ``loss, local_sum, gp1, seq = step(p1, p2)`` launches sweep +
     finish (per-pair losses, their local sum, the gradient w.r.t. p1 -- the upstream gradient is the constant 1 of
     ``.sum()`` / ``ttl_loss.backward()``, reference src/models/few_shot.py:110, src/trainNetwork.py:144) and the exchange;
-    ``step.global_sum(seq)`` is the all-reduced sum of step ``seq`` (with ``lag=1`` it is produced by the following step)."""
+    ``step.global_sum(seq)`` is the all-reduced sum of step ``seq`` (with ``lag=L`` it is produced L steps later; L <= PEER_RING/4)."""
 
     def __init__(self, B: int, N: int, M: int, device: torch.device, group: Optional[dist.ProcessGroup] = None, lag: int = 0):
         from . import _lib
@@ -154,8 +154,11 @@ class ShardedChamferStep:
         return self.out[2:], self.out[0], self.gp1, px.seq
 
     def flush(self) -> int:
-        """lag = 1: collect the last step's sum (nothing follows it that would). Returns its sequence number."""
-        self.exchange.collect(self.exchange.seq, torch.cuda.current_stream(self.device).cuda_stream)
+        """lag >= 1: collect the sums of the last ``lag`` steps (nothing follows them that would). Returns the sequence
+        number of the last step."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for s in range(max(1, self.exchange.seq - max(self.lag, 1) + 1), self.exchange.seq + 1):
+            self.exchange.collect(s, stream)
         return self.exchange.seq
 
     def global_sum(self, seq: int) -> torch.Tensor:

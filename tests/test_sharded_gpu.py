@@ -35,7 +35,7 @@ def _worker(rank, world, port, B, N, M, lag, out):
         lo, hi = shard_range(B, rank, world)
         step = ShardedChamferStep(hi - lo, N, M, dev, lag=lag)
         res = []
-        for it in range(6):  # more steps than the ring has slots
+        for it in range(19):  # more steps than the ring has slots
             p1, p2 = make_pair(B, N, M, seed=500 + it)
             a, b = p1[lo:hi].contiguous().to(dev), p2[lo:hi].contiguous().to(dev)
             loss, local_sum, gp1, seq = step(a, b)
@@ -50,10 +50,11 @@ def _worker(rank, world, port, B, N, M, lag, out):
             assert_close_rel(gp1.cpu().numpy(), ogp1[lo:hi], 1e-5, "grad_p1 of the shard")
             assert abs(float(local_sum) - float(oloss[lo:hi].astype(np.float64).sum())) <= 1e-5 * abs(float(oloss[lo:hi].sum()))
             res.append((want_seq, g, float(oloss.astype(np.float64).sum())))
-        if lag == 1:  # nothing follows the last step: an explicit flush collects its sum
+        if lag >= 1:  # nothing follows the last `lag` steps: an explicit flush collects their sums
             last = step.flush()
             torch.cuda.synchronize(dev)
-            res.append((last, float(step.global_sum(last)), None))
+            for sq in range(last - lag + 1, last + 1):
+                res.append((sq, float(step.global_sum(sq)), None))
         # the reduced value of step s is the oracle's sum over the WHOLE batch of step s (lag 1: delivered one step later)
         sums = {it + 1: r[2] for it, r in enumerate(res) if r[2] is not None}
         for want_seq, g, _ in res:
@@ -64,7 +65,7 @@ def _worker(rank, world, port, B, N, M, lag, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("lag", [0, 1])
+@pytest.mark.parametrize("lag", [0, 1, 3])
 def test_sharded_step_with_in_kernel_allreduce(lag):
     world = 2 if torch.cuda.device_count() >= 2 else 1
     B, N, M = 6, 300, 257
