@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfpsg_b200.so")
 LIB_TUNING = os.path.join(HERE, "libfpsg_b200_tuning.so")  # development build: FPSG_* ablation switches + timeline stamps
-SOURCES = ["api.cu", "chamfer_fwd.cu", "chamfer_finish.cu", "chamfer_bwd.cu", "pipeline.cu", "emd_sinkhorn.cu", "knn.cu", "edge_feature.cu", "pointcloud_io.cu"]
+SOURCES = ["api.cu", "chamfer_fwd.cu", "chamfer_finish.cu", "chamfer_bwd.cu", "pipeline.cu", "emd_sinkhorn.cu", "knn.cu", "knn_tc.cu", "edge_feature.cu", "pointcloud_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-cudart", "static", "-diag-suppress", "550"]
 

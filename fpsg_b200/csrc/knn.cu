@@ -14,6 +14,7 @@
 //                                                        subtraction is one rounding = fma(2, dot, -xx_j))
 // Ranking: larger pd first; equal pd ordered by ascending index (torch.topk leaves ties unspecified).
 #include "common.cuh"
+#include "knn_common.cuh"
 
 namespace fpsg {
 
@@ -338,37 +339,6 @@ knn_blocked_kernel(const float* __restrict__ x, const float* __restrict__ xx, in
 // (reverse, element-wise max, bitonic merge). Cost per buffered candidate ~5 instructions instead of ~35 for a
 // shuffle insertion.
 // ---------------------------------------------------------------------------------------------------------
-typedef unsigned long long u64;
-
-__device__ __forceinline__ unsigned f32_to_ord(float f) {
-    const unsigned u = __float_as_uint(f);
-    return u ^ (((int)u >> 31) | 0x80000000u);
-}
-__device__ __forceinline__ float ord_to_f32(unsigned o) {
-    return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
-}
-__device__ __forceinline__ u64 key_cmpx(u64 key, int d, bool take_max) {
-    const u64 o = __shfl_xor_sync(0xffffffffu, key, d);
-    const bool gt = key > o;
-    return (gt == take_max) ? key : o;
-}
-// sorts the warp's 32 keys descending by lane
-__device__ __forceinline__ u64 warp_sort_desc(u64 key, int lane) {
-#pragma unroll
-    for (int s = 2; s <= 32; s <<= 1) {
-        const bool desc = s == 32 ? true : ((lane & s) == 0);
-#pragma unroll
-        for (int d = s >> 1; d > 0; d >>= 1) key = key_cmpx(key, d, ((lane & d) == 0) == desc);
-    }
-    return key;
-}
-// bitonic sequence -> descending
-__device__ __forceinline__ u64 warp_merge_desc(u64 key, int lane) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) key = key_cmpx(key, d, (lane & d) == 0);
-    return key;
-}
-
 // Sorts up to 64 buffered candidate keys and merges them into the sorted list `key` (one entry per lane). Kept out
 // of line on purpose: eight inlined copies (one per query of the warp) overflow the instruction cache.
 __device__ __noinline__ u64 knn_flush_list(u64 key, const u64* buf, int cnt) {
@@ -631,12 +601,6 @@ constexpr int kSelColCap = 48;                  // candidate slots per thread co
 constexpr int kSelListStride = kSelCap + 2;     // u16 elements per query row of the candidate lists
 constexpr int kSelMaxN = 8192;                  // the cloud must fit shared memory as float4
 
-__device__ __forceinline__ float max3(float a, float b, float c) {
-    float r;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
-
 __device__ __forceinline__ float knn_pd3(const float4 q, const float xxi, const float4 c) {
     float dot = __fmul_rn(q.x, c.x);
     dot = __fmaf_rn(q.y, c.y, dot);
@@ -644,7 +608,6 @@ __device__ __forceinline__ float knn_pd3(const float4 q, const float xxi, const 
     return __fsub_rn(__fmaf_rn(2.0f, dot, c.w), xxi);
 }
 
-__device__ __forceinline__ u64 knn_key_of(float pd, int j) { return ((u64)f32_to_ord(pd) << 32) | (u64)(0xffffffffu - (unsigned)j); }
 
 // sorts two independent key sets at once (the two shuffle chains overlap: the stage is latency-bound otherwise)
 __device__ __forceinline__ void warp_sort_desc2(u64& a, u64& b, int lane) {
@@ -1221,8 +1184,14 @@ static KnnPlan make_knn_plan(int B, int C, int N, int k) {
     return p;
 }
 
+// knn_tc.cu: tensor-core pre-filter + exact re-scoring (generic C, k <= 32, 256 <= N <= 8192)
+bool knn_tc_eligible(int B, int C, int N, int k);
+size_t knn_tc_workspace(int B, int C, int N, int k);
+int knn_tc_launch(const float* x, int B, int C, int N, int k, int64_t* idx, void* ws, cudaStream_t stream);
+
 size_t knn_workspace(int B, int C, int N, int k) {
     if (B <= 0 || C < 1 || N < 1 || k < 1) return 0;
+    if (C != 3 && knn_tc_eligible(B, C, N, k)) return knn_tc_workspace(B, C, N, k);
     return make_knn_plan(B, C, N, k).ws_bytes;
 }
 
@@ -1291,6 +1260,12 @@ int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx,
     if (B == 0) return FPSG_OK;
     if (!x || !idx) return fail(FPSG_EINVAL, "knn: null pointer");
     if (B > 65535) return fail(FPSG_EINVAL, "knn: B > 65535 not supported in one call");
+    if (C != 3 && knn_tc_eligible(B, C, N, k)) {
+        const size_t need = knn_tc_workspace(B, C, N, k);
+        if (!ws || ws_bytes < need) return fail(FPSG_EWORKSPACE, "knn: workspace of %zu bytes required, %zu given", need, ws ? ws_bytes : (size_t)0);
+        if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return fail(FPSG_EINVAL, "knn: the workspace must be 16-byte aligned");
+        return knn_tc_launch(x, B, C, N, k, idx, ws, stream);
+    }
     if ((size_t)C * 32 * sizeof(float) > 160 * 1024) return fail(FPSG_EINVAL, "knn: C=%d too large", C);
     const KnnPlan p = make_knn_plan(B, C, N, k);
     if (p.smem > 227 * 1024) return fail(FPSG_EINVAL, "knn: C=%d with k=%d needs %zu bytes of shared memory per CTA (limit 227 KB)", C, k, p.smem);
