@@ -222,7 +222,10 @@ def secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M)
         wsk = torch.empty(max(nbk, 1), dtype=torch.uint8, device=dev)
         us = _timed_us(torch, stream, dev, lambda: _lib.check(L.fpsg_knn_fwd(xk.data_ptr(), 32, C_, 1024, 20, ik.data_ptr(), wsk.data_ptr(), nbk, sp)), 20)
         tf = (2 * C_ + 2) * 32 * 1024 * 1024 / us / 1e6
-        sec[f"c3_knn_k20_B32_N1024_C{C_}"] = {"us_per_call": us, "clouds_per_s": 32 / us * 1e6, "tflops": tf, "frac_of_fp32_peak": tf / fp32_peak_tflops}
+        sec[f"c3_knn_k20_B32_N1024_C{C_}"] = {"us_per_call": us, "clouds_per_s": 32 / us * 1e6, "tflops": tf, "frac_of_fp32_peak": tf / fp32_peak_tflops,
+                                             "path": "FP32 threshold-selection kernel (knn.cu)" if C_ == 3 else
+                                                     "tcgen05 FP16 pre-filter + exact FP32 re-scoring of the marked candidates (knn_tc.cu); tflops = the "
+                                                     "algorithmic (2C+2) N^2 FLOP of the reference's matmul formulation over the time, not an FP32 rate"}
         del xk, ik, wsk
 
     # ---- c2: one training step of 32 episodes = 32 x (5 query + 32 support) = 1184 pairs, N=M=2048

@@ -37,9 +37,11 @@ if B * N * N <= 64 << 20:
     for c in range(C):
         xx32 = (xx32 + (x.numpy()[:, c, :] * x.numpy()[:, c, :]).astype(np.float32)).astype(np.float32)
     want = np.einsum("bci,bcj->bij", xn, xn) - xx32.astype(np.float64)[:, None, :] / 2
-    err = np.abs(s - want)
     mx = xx32.max(axis=1)
-    E = 2.0 ** -8 * np.sqrt(xx32.astype(np.float64) * mx[:, None]) + 2.0 ** -16 * mx[:, None]
+    sc = np.array([2.0 ** (7 - np.frexp(np.sqrt(np.float32(m)))[1]) if m > 0 else 1.0 for m in mx])  # the operand scale of the kernel
+    s = s / (sc * sc)[:, None, None]
+    err = np.abs(s - want)
+    E = 1.25 * 2.0 ** -10 * np.sqrt(xx32.astype(np.float64) * mx[:, None]) + 2.0 ** -16 * mx[:, None]
     res["scores_nan"] = int(np.isnan(s).sum())
     res["max_abs_err"] = float(np.nanmax(err))
     res["max_err_over_E"] = float(np.nanmax(err / E[:, :, None]))

@@ -56,4 +56,8 @@ def get_graph_feature(x: torch.Tensor, k: int = 20, idx: torch.Tensor | None = N
         if idx.dtype != torch.int64 or idx.dim() != 3 or idx.shape[0] != B or idx.shape[1] != N:
             raise RuntimeError(f"idx must be int64 of shape (B, N, k), got {idx.dtype} {tuple(idx.shape)}")
         idx = idx.to(x.device).contiguous()
+        # a caller-supplied index is range-checked (the reference's gather raises an indexing error; the kernels do not check):
+        # one host synchronisation, on this path only -- DGCNNfeat.forward never passes idx
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= N):
+            raise IndexError(f"idx values must lie in [0, {N}), got [{int(idx.min())}, {int(idx.max())}]")
     return _GraphFeature.apply(x, idx)

@@ -84,3 +84,17 @@ def test_c3_layer_shapes():
         idx = fpsg_b200.knn(x.detach(), 20)
         indeg = torch.zeros(4, 1024, device="cuda").scatter_add_(1, idx.reshape(4, -1), torch.ones(4, 1024 * 20, device="cuda"))
         assert torch.allclose(x.grad, indeg[:, None, :].expand(-1, C, -1), rtol=0, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_out_of_range_idx_is_rejected():
+    """A caller-supplied idx outside [0, N) raises (the reference's gather fails on it too) instead of reading out of bounds."""
+    import fpsg_b200
+    x = torch.randn(2, 8, 50, device="cuda")
+    idx = torch.randint(0, 50, (2, 50, 5), device="cuda")
+    idx[1, 3, 2] = 50
+    with pytest.raises(IndexError):
+        fpsg_b200.get_graph_feature(x, k=5, idx=idx)
+    idx[1, 3, 2] = -1
+    with pytest.raises(IndexError):
+        fpsg_b200.get_graph_feature(x, k=5, idx=idx)
