@@ -324,7 +324,8 @@ struct TcArgs {
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_aux, const TcArgs a) {
     extern __shared__ unsigned char tc_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (128-byte swizzle) by an OFFSET from the shared array: the pointers keep their address space (LDS / STS)
+    unsigned char* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = base;                    // the query tile: [NK] chunks of 128 rows x 128 B (128-byte swizzle), then 128 rows x 32 B
     unsigned char* sB = sA + a.a_bytes;          // [stages] a candidate block: [NK] chunks of 256 rows x 128 B, then 256 rows x 32 B
     float* sGm = reinterpret_cast<float*>(sB + (size_t)a.stages * a.stage_bytes);  // [32 groups][256 row halves]
