@@ -252,6 +252,33 @@ def secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M)
                                                        ws2.data_ptr(), nb2, sp))
     sec["c2_B1184_as_64_calls"] = chamfer_entry(_timed_us(torch, stream, dev, c2_as_issued, 5, 2), B2, N, M)
 
+    # the same 64 calls, issued round-robin over three lanes (a stream + workspace each; outputs are disjoint slices anyway):
+    # the calls of a training step are independent, so the 5-pair calls and the tails of the 32-pair calls overlap their neighbours
+    nb37 = L.fpsg_chamfer_fwd_workspace_bytes(32, N, M)
+    lane_s = [torch.cuda.Stream(device=dev) for _ in range(N_LANES)]
+    lane_ws = [torch.empty(nb37, dtype=torch.uint8, device=dev) for _ in range(N_LANES)]
+
+    def c2_as_issued_lanes():
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        for st_ in lane_s:
+            st_.wait_event(ev)
+        c = 0
+        for e in range(32):
+            o5, o32 = e * 37, e * 37 + 5
+            for off, nb_ in ((o5, 5), (o32, 32)):
+                ln = c % N_LANES
+                c += 1
+                _lib.check(L.fpsg_chamfer_loss_fwd_bwd(a2 + off * N * 12, b2 + off * M * 12, nb_, N, M, 1.0, 1.0, None, lo.data_ptr() + 4 * off, None, None,
+                                                       ip + 8 * off * N, ip + 8 * (B2 * N + off * M), gp.data_ptr() + off * N * 12, None,
+                                                       lane_ws[ln].data_ptr(), nb37, lane_s[ln].cuda_stream))
+        for st_ in lane_s:
+            e2_ = torch.cuda.Event()
+            e2_.record(st_)
+            stream.wait_event(e2_)
+    sec["c2_B1184_as_64_calls_3_lanes"] = chamfer_entry(_timed_us(torch, stream, dev, c2_as_issued_lanes, 5, 2), B2, N, M)
+    del lane_ws
+
     sg2 = (_lib.ChamferSegment * 2)()
     sg2[0].p1, sg2[0].p2, sg2[0].gp1, sg2[0].gp2, sg2[0].batch, sg2[0].weight = a2, b2, gp.data_ptr(), None, 5, 1.0
     sg2[1].p1, sg2[1].p2, sg2[1].gp1, sg2[1].gp2 = a2 + 5 * N * 12, b2 + 5 * M * 12, gp.data_ptr() + 5 * N * 12, None
