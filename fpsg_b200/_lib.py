@@ -80,6 +80,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.fpsg_chamfer_pipeline_create.argtypes = [c_int, c_int, c_int, c_float, c_float, c_int, vp, c_size_t, vp, c_size_t, vpp]
     L.fpsg_chamfer_pipeline_submit.restype = c_int
     L.fpsg_chamfer_pipeline_submit.argtypes = [vp, vp, vp]
+    L.fpsg_chamfer_pipeline_submit_device.restype = c_int
+    L.fpsg_chamfer_pipeline_submit_device.argtypes = [vp, vp, vp, vp]
     L.fpsg_chamfer_pipeline_result.restype = c_int
     L.fpsg_chamfer_pipeline_result.argtypes = [vp, ctypes.POINTER(c_float), vp, vpp, vpp, vpp]
     L.fpsg_chamfer_pipeline_set_exchange.restype = c_int

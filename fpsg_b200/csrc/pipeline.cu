@@ -118,21 +118,10 @@ int fpsg_chamfer_pipeline_create(int B, int N, int M, float w1, float w2, int de
     return FPSG_OK;
 }
 
-int fpsg_chamfer_pipeline_submit(fpsg_chamfer_pipeline_t* p, const float* p1_host, const float* p2_host) {
-    if (!p || !p1_host || !p2_host) return fail(FPSG_EINVAL, "pipeline_submit: null argument");
-    if (p->head - p->tail >= p->depth) return fail(FPSG_EINVAL, "pipeline_submit: %d batches in flight, take a result first", p->depth);
-    const int s = (int)(p->head % p->depth);
+// the compute part of a submit: sweep + finish on the slot's lane, D2H copy of the result record, `done` event
+static int pipeline_launch_step(fpsg_chamfer_pipeline* p, int s, const float* d1, const float* d2) {
     char* slot = p->dev + (size_t)s * p->L.slot_bytes;
-    float* d1 = reinterpret_cast<float*>(slot + p->L.in_off);
-    float* d2 = d1 + (size_t)p->B * p->N * 3;
-    // the slot's inputs are free again once the step that last used them has run (its `done` event: the caller took that
-    // result before this slot could come round again, so the event is long complete -- the wait costs nothing)
-    if (p->head >= p->depth) FPSG_CUDA_OK(cudaStreamWaitEvent(p->copy, p->done[s], 0));
-    FPSG_CUDA_OK(cudaMemcpyAsync(d1, p1_host, (size_t)p->B * p->N * 3 * sizeof(float), cudaMemcpyHostToDevice, p->copy));
-    FPSG_CUDA_OK(cudaMemcpyAsync(d2, p2_host, (size_t)p->B * p->M * 3 * sizeof(float), cudaMemcpyHostToDevice, p->copy));
-    FPSG_CUDA_OK(cudaEventRecord(p->copied[s], p->copy));
     cudaStream_t compute = p->compute[s];
-    FPSG_CUDA_OK(cudaStreamWaitEvent(compute, p->copied[s], 0));
     float* gp1 = reinterpret_cast<float*>(slot + p->L.gp1_off);
     int64_t* idx1 = reinterpret_cast<int64_t*>(slot + p->L.idx_off);
     float* outrec = reinterpret_cast<float*>(slot + p->L.out_off);  // totals[2], then loss[B]
@@ -149,6 +138,33 @@ int fpsg_chamfer_pipeline_submit(fpsg_chamfer_pipeline_t* p, const float* p1_hos
     FPSG_CUDA_OK(cudaEventRecord(p->done[s], compute));
     ++p->head;
     return FPSG_OK;
+}
+
+int fpsg_chamfer_pipeline_submit(fpsg_chamfer_pipeline_t* p, const float* p1_host, const float* p2_host) {
+    if (!p || !p1_host || !p2_host) return fail(FPSG_EINVAL, "pipeline_submit: null argument");
+    if (p->head - p->tail >= p->depth) return fail(FPSG_EINVAL, "pipeline_submit: %d batches in flight, take a result first", p->depth);
+    const int s = (int)(p->head % p->depth);
+    char* slot = p->dev + (size_t)s * p->L.slot_bytes;
+    float* d1 = reinterpret_cast<float*>(slot + p->L.in_off);
+    float* d2 = d1 + (size_t)p->B * p->N * 3;
+    // the slot's inputs are free again once the step that last used them has run (its `done` event: the caller took that
+    // result before this slot could come round again, so the event is long complete -- the wait costs nothing)
+    if (p->head >= p->depth) FPSG_CUDA_OK(cudaStreamWaitEvent(p->copy, p->done[s], 0));
+    FPSG_CUDA_OK(cudaMemcpyAsync(d1, p1_host, (size_t)p->B * p->N * 3 * sizeof(float), cudaMemcpyHostToDevice, p->copy));
+    FPSG_CUDA_OK(cudaMemcpyAsync(d2, p2_host, (size_t)p->B * p->M * 3 * sizeof(float), cudaMemcpyHostToDevice, p->copy));
+    FPSG_CUDA_OK(cudaEventRecord(p->copied[s], p->copy));
+    FPSG_CUDA_OK(cudaStreamWaitEvent(p->compute[s], p->copied[s], 0));
+    return pipeline_launch_step(p, s, d1, d2);
+}
+
+int fpsg_chamfer_pipeline_submit_device(fpsg_chamfer_pipeline_t* p, const float* p1_device, const float* p2_device, fpsg_stream_t producer_stream) {
+    if (!p || !p1_device || !p2_device) return fail(FPSG_EINVAL, "pipeline_submit_device: null argument");
+    if (p->head - p->tail >= p->depth) return fail(FPSG_EINVAL, "pipeline_submit_device: %d batches in flight, take a result first", p->depth);
+    const int s = (int)(p->head % p->depth);
+    // the lane starts behind whatever the producer's stream holds now (the kernels that wrote p1 / p2)
+    FPSG_CUDA_OK(cudaEventRecord(p->copied[s], static_cast<cudaStream_t>(producer_stream)));
+    FPSG_CUDA_OK(cudaStreamWaitEvent(p->compute[s], p->copied[s], 0));
+    return pipeline_launch_step(p, s, p1_device, p2_device);
 }
 
 int fpsg_chamfer_pipeline_result(fpsg_chamfer_pipeline_t* p, float* loss_sum_host, float* loss_host, const float** gp1_device,

@@ -59,6 +59,17 @@ class ChamferPipeline:
         _lib.check(_lib.lib().fpsg_chamfer_pipeline_submit(self._h, p1_host.data_ptr(), p2_host.data_ptr()))
         self._keep.append((p1_host, p2_host))
 
+    def submit_device(self, p1: torch.Tensor, p2: torch.Tensor) -> None:
+        """The same step for tensors that are already on the device (e.g. the decoder's output): no copies; the lane's kernels
+        are ordered behind the current stream. ``p1`` / ``p2`` must not be modified until the batch's ``result()``."""
+        for name, t, n in (("p1", p1, self.N), ("p2", p2, self.M)):
+            if t.device != self.device or t.dtype != torch.float32 or tuple(t.shape) != (self.B, n, 3) or not t.is_contiguous():
+                raise RuntimeError(f"{name} must be a contiguous float32 tensor of shape ({self.B}, {n}, 3) on {self.device}, "
+                                   f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().fpsg_chamfer_pipeline_submit_device(self._h, p1.data_ptr(), p2.data_ptr(), stream))
+        self._keep.append((p1, p2))
+
     def result(self):
         _lib.check(_lib.lib().fpsg_chamfer_pipeline_result(self._h, ctypes.byref(self._sum), self._loss.data_ptr(), ctypes.byref(self._gp), None, None))
         self._keep.pop(0)

@@ -182,6 +182,11 @@ int fpsg_chamfer_pipeline_create(int B, int N, int M, float w1, float w2, int de
                                  size_t device_bytes, void* pinned_host_arena, size_t pinned_host_bytes,
                                  fpsg_chamfer_pipeline_t** out);
 int fpsg_chamfer_pipeline_submit(fpsg_chamfer_pipeline_t* p, const float* p1_host, const float* p2_host);
+/* The same step for inputs that are already on the DEVICE (the decoder's output, src/models/few_shot.py:106-110): no copies;
+ * the lane's kernels are ordered behind everything `producer_stream` holds at the time of the call. p1 (B,N,3) / p2 (B,M,3)
+ * must stay unchanged until the batch's result was taken. Host and device submits may be mixed. */
+int fpsg_chamfer_pipeline_submit_device(fpsg_chamfer_pipeline_t* p, const float* p1_device, const float* p2_device,
+                                        fpsg_stream_t producer_stream);
 int fpsg_chamfer_pipeline_result(fpsg_chamfer_pipeline_t* p, float* loss_sum_host, float* loss_host,
                                  const float** gp1_device, const int64_t** idx1_device, const int64_t** idx2_device);
 /* Multi-GPU: every batch of this pipeline takes part in the scalar exchange above with lag = depth (seq = the batch's

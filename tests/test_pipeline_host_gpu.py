@@ -46,6 +46,33 @@ def test_pipeline_matches_oracle_under_interleaving(B, N, M, depth, pinned):
     pipe.close()
 
 
+def test_pipeline_device_submits_match_oracle_and_mix_with_host_submits():
+    """`submit_device`: inputs already on the GPU (the decoder's output in the reference), no copies, same lanes."""
+    import fpsg_b200
+    B, N, M, depth = 4, 700, 513, 3
+    pipe = fpsg_b200.ChamferPipeline(B, N, M, depth=depth)
+    batches = [make_pair(B, N, M, seed=300 + s) for s in range(7)]
+    want = [_oracle_step(a, b, 1.0, 1.0) for a, b in batches]
+    dev = [(a.cuda(), b.cuda()) for a, b in batches]
+    got, nxt = [], 0
+    while len(got) < len(batches):
+        while nxt < len(batches) and pipe.in_flight < depth:
+            if nxt % 3 == 2:
+                pipe.submit(*batches[nxt])          # a host batch between device batches
+            else:
+                pipe.submit_device(*dev[nxt])
+            nxt += 1
+        s, loss, gp1 = pipe.result()
+        got.append((s, loss.clone().numpy(), gp1.cpu().numpy()))
+    for (s, loss, gp1), (oloss, ogp1) in zip(got, want):
+        assert_close_rel(loss, oloss, 1e-6, "loss")
+        assert abs(s - oloss.sum()) <= 1e-5 * abs(oloss.sum())
+        assert_close_rel(gp1, ogp1, 1e-5, "grad_p1")
+    with pytest.raises(RuntimeError):
+        pipe.submit_device(batches[0][0], dev[0][1])  # a CPU tensor is not a device buffer
+    pipe.close()
+
+
 def test_pipeline_argument_errors():
     import fpsg_b200
     from fpsg_b200._lib import FpsgError
