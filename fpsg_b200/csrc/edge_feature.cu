@@ -329,7 +329,7 @@ int edge_feature_backward_launch(const float* g, const int64_t* idx, int B, int 
     FPSG_CUDA_OK(cudaGetLastError());
     const long long nk = (long long)N * k;
     const size_t psmem = edge_plane_smem(N, k);
-    if (nk <= 65535 && (k & 3) == 0 && k <= 4 * kPlaneK4 && N <= kPlaneThreads && psmem <= 212 * 1024 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && !getenv("FPSG_EDGE_NOPLANE")) {
+    if (nk <= 65535 && (k & 3) == 0 && k <= 4 * kPlaneK4 && N <= kPlaneThreads && psmem <= 212 * 1024 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && !tune_env("FPSG_EDGE_NOPLANE")) {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long planes = (long long)B * C;

@@ -9,6 +9,9 @@ from . import _lib
 from .chamfer import _device_guard, _stream_ptr
 
 
+_MAX_CLOUDS_PER_CALL = 65535
+
+
 def knn(x: torch.Tensor, k: int) -> torch.Tensor:
     if not isinstance(x, torch.Tensor):
         raise TypeError(f"x must be a torch.Tensor, got {type(x).__name__}")
@@ -31,9 +34,13 @@ def knn(x: torch.Tensor, k: int) -> torch.Tensor:
         return idx
     L = _lib.lib()
     with _device_guard(x.device):
-        nbytes = L.fpsg_knn_workspace_bytes(B, C, N, k)
-        ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=x.device)
-        rc = L.fpsg_knn_fwd(x.data_ptr(), B, C, N, k, idx.data_ptr(), ws.data_ptr(), nbytes,
-                            _stream_ptr(x.device))
-        _lib.check(rc)
+        # one call of the library takes at most 65535 clouds (a grid dimension); larger batches go in chunks, as the reference's
+        # torch ops accept any batch size
+        for b0 in range(0, B, _MAX_CLOUDS_PER_CALL):
+            nb = min(_MAX_CLOUDS_PER_CALL, B - b0)
+            nbytes = L.fpsg_knn_workspace_bytes(nb, C, N, k)
+            ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=x.device)
+            rc = L.fpsg_knn_fwd(x.data_ptr() + 4 * b0 * C * N, nb, C, N, k, idx.data_ptr() + 8 * b0 * N * k, ws.data_ptr(), nbytes,
+                                _stream_ptr(x.device))
+            _lib.check(rc)
     return idx

@@ -118,3 +118,15 @@ def test_knn_error_behaviour():
     with pytest.raises(RuntimeError):
         fpsg_b200.knn(x.double(), 4)
     assert fpsg_b200.knn(x[:0], 4).shape == (0, 16, 4)
+
+
+def test_knn_batches_beyond_one_call_are_chunked(monkeypatch):
+    """The library takes at most 65535 clouds per call; the wrapper chunks (checked with a small chunk size)."""
+    import fpsg_b200
+    import sys
+    K = sys.modules["fpsg_b200.knn"]  # the module (the package attribute of that name is the function)
+    O = _oracle()
+    x = make_cloud_cn(7, 3, 60, seed=21)
+    monkeypatch.setattr(K, "_MAX_CLOUDS_PER_CALL", 3)
+    got = fpsg_b200.knn(x.cuda(), 5).cpu().numpy()
+    assert (got == O.knn_f32(x.numpy(), 5)).all()
