@@ -34,6 +34,11 @@ import sys
 import threading
 import time
 
+# The step is issued over several streams (lanes) and the host-buffer pipeline owns 1 + depth more: with the default of 8
+# hardware work queues, streams get aliased onto shared queues and falsely serialise each other (measured: e2e 410-560 k
+# pairs/s instead of 715 k). Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -41,7 +46,7 @@ B_PER_GPU, N_PTS, M_PTS = 32, 2048, 2048
 WORKLOAD = "c1: Chamfer loss fwd+bwd(p1), B=32 per GPU, N=M=2048, synthetic xyz float32"
 METRIC = "chamfer_fwd_bwd_pairs_per_s"
 RING_SETS = 96  # distinct input batches cycled through: 96 x 1.57 MB = 151 MB > 126 MB L2
-N_LANES = 3     # streams (each with its own workspace and outputs) the independent steps are issued over, round-robin
+N_LANES = 4     # streams (each with its own workspace and outputs) the independent steps are issued over, round-robin
 # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch, from the ncu --set full capture named below (the
 # kernel streams its 1.573 MB of input once; a number taken under the profiler is cited, not re-measured in the timed run)
 SWEEP_DRAM_TRAFFIC_BYTES = 1.599e6
@@ -252,7 +257,7 @@ def secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M)
                                                        ws2.data_ptr(), nb2, sp))
     sec["c2_B1184_as_64_calls"] = chamfer_entry(_timed_us(torch, stream, dev, c2_as_issued, 5, 2), B2, N, M)
 
-    # the same 64 calls, issued round-robin over three lanes (a stream + workspace each; outputs are disjoint slices anyway):
+    # the same 64 calls, issued round-robin over N_LANES lanes (a stream + workspace each; outputs are disjoint slices anyway):
     # the calls of a training step are independent, so the 5-pair calls and the tails of the 32-pair calls overlap their neighbours
     nb37 = L.fpsg_chamfer_fwd_workspace_bytes(32, N, M)
     lane_s = [torch.cuda.Stream(device=dev) for _ in range(N_LANES)]
@@ -276,7 +281,7 @@ def secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M)
             e2_ = torch.cuda.Event()
             e2_.record(st_)
             stream.wait_event(e2_)
-    sec["c2_B1184_as_64_calls_3_lanes"] = chamfer_entry(_timed_us(torch, stream, dev, c2_as_issued_lanes, 5, 2), B2, N, M)
+    sec[f"c2_B1184_as_64_calls_{N_LANES}_lanes"] = chamfer_entry(_timed_us(torch, stream, dev, c2_as_issued_lanes, 5, 2), B2, N, M)
     del lane_ws
 
     sg2 = (_lib.ChamferSegment * 2)()
@@ -588,12 +593,12 @@ def main():
 
     # ---- end to end, headline: the host-buffer call of the C ABI (fpsg_chamfer_pipeline_*, fpsg_b200.ChamferPipeline): every
     # step copies ITS inputs from pinned host memory (H2D, 1.57 MB), runs the fused loss step and reads its losses back
-    # (D2H); up to 3 steps are in flight, so the copies of step i+1 overlap the kernels of step i ----
+    # (D2H); up to 4 steps are in flight (one lane each), so the copies of step i+1 overlap the kernels of step i ----
     host = []
     for s_ in range(8):
         h1, h2 = make_inputs(B, N, M, seed=777 + 1000 * rank + s_, pin=True)
         host.append((h1, h2))
-    DEPTH = 3
+    DEPTH = int(os.environ.get("FPSG_BENCH_DEPTH", "4"))  # = lanes of the pipeline (measured: 261 / 494 / 640 / 715 / 732 k pairs/s at depth 1 / 2 / 3 / 4 / 6, profiles/r02b_e2e_depth.json)
     pipe = fpsg_b200.ChamferPipeline(B, N, M, device=dev, depth=DEPTH)
     e2e_exchange = None
     if exchange is not None:  # N > 1: every step of the pipeline takes part in the in-kernel scalar all-reduce (lag 1)
@@ -683,7 +688,7 @@ def main():
             "e2e": {"value": pairs * e2e_steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": (2 + B) * 4,
                     "steps": e2e_steps,
                     "api": "fpsg_chamfer_pipeline_submit / _result (include/fpsg_b200.h; fpsg_b200.ChamferPipeline): every step copies its own inputs "
-                           "from pinned HOST memory, runs sweep + finish and reads its per-pair losses and their sum back to the host; depth 3, so the "
+                           "from pinned HOST memory, runs sweep + finish and reads its per-pair losses and their sum back to the host; depth 4, so the "
                            "H2D copies of step i+1 overlap the kernels of step i; the gradient stays on the device as in the reference"},
             "e2e_autograd": {"value": pairs * ag_steps / ag_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": 4,
                              "steps": ag_steps,

@@ -169,6 +169,8 @@ int fpsg_peer_exchange_collect(const fpsg_peer_exchange_t* px, fpsg_stream_t str
  * slots is a LANE of its own -- its own compute stream, workspace and outputs -- so with depth >= 2 the copies of batch
  * i+1 overlap the kernels of batch i, and the latency-bound tail of batch i (merge, arg-min recovery, backward) overlaps
  * the distance sweep of batch i+1 (measured at B=32, N=M=2048: 56 us per batch on one lane, 44.6 us on three).
+ * (Run the process with CUDA_DEVICE_MAX_CONNECTIONS >= the number of streams in use, e.g. 32: with the default of 8 hardware
+ * queues the lanes may alias onto shared queues and serialise.)
  * Up to `depth` (1..8; 1..4 with an exchange) batches may be in flight; the host buffers of
  * a batch must stay valid until its result was taken. The caller owns all memory: a 256-byte aligned DEVICE arena and
  * a PINNED HOST arena of the sizes fpsg_chamfer_pipeline_arena_bytes reports, both alive as long as the handle; the
