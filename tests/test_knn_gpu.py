@@ -48,7 +48,9 @@ def test_knn_bit_exact_vs_oracle(B, C, N, k):
     (1, 64, 1024, 100), (1, 128, 600, 128), (2, 32, 2100, 70),   # knn_kernel<4,false>, several candidate tiles (lists live in shared memory between tiles)
     (1, 64, 1024, 50), (1, 128, 600, 64),                         # knn_blocked_kernel<2>, several tiles
     (1, 3, 5000, 100), (1, 3, 3000, 40),                          # knn_kernel<4,true> / <2,true>
-    (1, 64, 2500, 20),                                            # generic C beyond the scratch-row kernel: knn_gemm_kernel
+    (1, 64, 2500, 20),                                            # tensor-core path (knn_tc.cu), several 256-candidate blocks and tiles
+    (1, 20, 2500, 20),                                            # generic C outside the tensor-core range, beyond the scratch-row kernel: knn_gemm_kernel
+    (2, 20, 900, 20),                                             # ... inside it: knn_rows_kernel + knn_rows_select_kernel
     (1, 3, 9000, 32), (1, 450, 200, 20),                          # knn_bulk_kernel<true> / <false> (C too large for the register-tiled kernels)
 ])
 def test_knn_every_dispatch_path_multi_tile(B, C, N, k):
