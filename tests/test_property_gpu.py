@@ -65,3 +65,46 @@ def test_knn_random_shapes_match_oracle(B, C, N, kfrac, kind, seed):
     got = fpsg_b200.knn(torch.from_numpy(np.ascontiguousarray(x)).cuda(), k).cpu().numpy()
     ref = O.knn_f32(np.ascontiguousarray(x), k)
     assert (got == ref).all(), f"B={B} C={C} N={N} k={k} kind={kind}: {(got != ref).sum()} positions differ"
+
+
+TC_KINDS = ["normal", "grid", "dup", "offset", "scaled", "relu", "clusters", "lowrank"]
+
+
+def _features(rng, B, C, N, kind):
+    """Feature clouds (B,C,N) that stress the tensor-core pre-filter's error bound (knn_tc.cu): exact ties (grid / dup), norms much
+    larger than distances (offset), extreme magnitudes (scaled: the per-cloud FP16 scaling), post-activation features (relu),
+    tight clusters far apart (near-ties inside, huge gaps between), features that live in a few directions (lowrank)."""
+    x = rng.standard_normal((B, C, N)).astype(np.float32)
+    if kind == "grid":
+        return rng.integers(-2, 3, size=(B, C, N)).astype(np.float32)
+    if kind == "dup":
+        base = rng.standard_normal((B, C, max(1, N // 5 + 1))).astype(np.float32)
+        return np.take_along_axis(base, rng.integers(0, base.shape[2], size=(B, 1, N)).repeat(C, axis=1), axis=2)
+    if kind == "offset":
+        return (x * np.float32(rng.choice([0.01, 0.3, 1.0])) + np.float32(rng.choice([5.0, 40.0, 300.0]))).astype(np.float32)
+    if kind == "scaled":
+        return (x * np.float32(10.0 ** rng.integers(-12, 13))).astype(np.float32)
+    if kind == "relu":
+        return np.where(x > 0, x, np.float32(0.2) * x).astype(np.float32) * np.float32(3.0)
+    if kind == "clusters":
+        centres = (rng.standard_normal((B, C, 6)) * 20).astype(np.float32)
+        pick = rng.integers(0, 6, size=(B, 1, N)).repeat(C, axis=1)
+        return (np.take_along_axis(centres, pick, axis=2) + x * np.float32(1e-3)).astype(np.float32)
+    if kind == "lowrank":
+        basis = rng.standard_normal((B, C, 3)).astype(np.float32)
+        coef = rng.standard_normal((B, 3, N)).astype(np.float32)
+        return np.einsum("bcr,brn->bcn", basis, coef).astype(np.float32)
+    return x
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(B=st.integers(1, 3), C=st.sampled_from([16, 24, 32, 64, 64, 72, 128]), N=st.integers(256, 1300), k=st.integers(1, 32),
+       kind=st.sampled_from(TC_KINDS), seed=st.integers(0, 2 ** 20))
+def test_knn_tensor_core_path_random_inputs_match_oracle(B, C, N, k, kind, seed):
+    """Shapes inside the tensor-core path's range, value distributions chosen against its error bound: bit-exact or bust."""
+    from oracle import cpu_oracle as O
+    import fpsg_b200
+    x = np.ascontiguousarray(_features(np.random.default_rng(seed), B, C, N, kind))
+    got = fpsg_b200.knn(torch.from_numpy(x).cuda(), k).cpu().numpy()
+    ref = O.knn_f32(x, k)
+    assert (got == ref).all(), f"B={B} C={C} N={N} k={k} kind={kind} seed={seed}: {(got != ref).sum()} positions differ"
