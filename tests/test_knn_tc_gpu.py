@@ -62,3 +62,36 @@ def test_knn_tensor_core_path_non_finite_inputs_terminate():
     idx = fpsg_b200.knn(x.cuda(), 20)
     torch.cuda.synchronize()
     assert int(idx.min()) >= 0 and int(idx.max()) < 512
+
+
+def test_knn_tensor_core_path_is_cuda_graph_capturable():
+    """The tensor-core kNN call (memset node, four kernels, two TMA tensor maps passed by value) captured in a CUDA graph and
+    replayed on new data in the same buffers gives the oracle's result: no allocation, no host synchronisation inside."""
+    from fpsg_b200 import _lib
+    from oracle import cpu_oracle as O
+    L = _lib.lib()
+    B, C, N, k = 2, 64, 700, 20
+    x1, x2 = make_cloud_cn(B, C, N, seed=71), make_cloud_cn(B, C, N, seed=72) * 7.0
+    dev = torch.device("cuda")
+    x = x1.to(dev)
+    idx = torch.empty(B, N, k, dtype=torch.int64, device=dev)
+    nb = L.fpsg_knn_workspace_bytes(B, C, N, k)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+
+    def enqueue(stream):
+        _lib.check(L.fpsg_knn_fwd(x.data_ptr(), B, C, N, k, idx.data_ptr(), ws.data_ptr(), nb, stream))
+
+    enqueue(torch.cuda.current_stream().cuda_stream)  # warm-up outside capture (function attributes, driver entry point)
+    torch.cuda.synchronize()
+    assert (idx.cpu().numpy() == O.knn_f32(x1.numpy(), k)).all()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        enqueue(torch.cuda.current_stream().cuda_stream)
+    x.copy_(x2)
+    idx.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert (idx.cpu().numpy() == O.knn_f32(x2.numpy(), k)).all(), "replayed graph differs from the oracle"
+    graph.replay()  # and again: the workspace is reused without any re-initialisation by the host
+    torch.cuda.synchronize()
+    assert (idx.cpu().numpy() == O.knn_f32(x2.numpy(), k)).all()
