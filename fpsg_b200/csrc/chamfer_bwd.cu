@@ -57,7 +57,8 @@ chamfer_bwd_kernel(const SegTable seg, BwdSide s1, BwdSide s2, bool uniform, boo
     const BwdSide& S = first ? s1 : s2;
     const int blk = first ? blockIdx.x : blockIdx.x - s1.blocks;
     const int b = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // (the warp index through a shuffle: the compiler then treats it, and the branches on it, as warp-uniform)
+    const int tid = threadIdx.x, lane = tid & 31, w = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int i0 = blk * kBwdThreads;
     const int i = i0 + tid;
     const bool live = i < S.Na;

@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishClusterMax + 64, 2) 
     // sub-partition -- exactly what ONE retiring sweep CTA (4 warps x 128 threads x 128 registers) frees there. The finish
     // CTAs then become resident, stage their clouds and start polling while the rest of the sweep is still running.
     const int nthreads = blockDim.x;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nwarps = nthreads >> 5;
+    // (the warp index through a shuffle: the compiler then treats it, and the branches on it, as warp-uniform)
+    const int tid = threadIdx.x, lane = tid & 31, w = __shfl_sync(0xffffffffu, tid >> 5, 0), nwarps = nthreads >> 5;
     constexpr bool worker = true;
 
     const int sg = a.seg.n == 1 ? 0 : seg_find(a.seg, b);
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishClusterMax + 64, 2) 
 
     // loss partials of this warp (fixed-order shuffle tree in double); pushed to cluster rank 0 in step 3
     double ls1 = rvalid ? (double)mr : 0.0, ls2 = cvalid ? (double)mc : 0.0;
+    __syncwarp();  // tells the compiler the warp is converged here: the 20 shuffles below need no convergence wrappers (~16 instructions each)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ls1 += __shfl_down_sync(0xffffffffu, ls1, o);

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
     __shared__ int sFound[kFinThreads];
     __shared__ double sRed[kFinThreads / 32];
 
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, w = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
     // pair-fastest grid: CTAs are dispatched block row by block row, i.e. all row blocks (the long ones: ~20 partials per
     // row) of all pairs before any column block. The CTAs that only become resident when the last sweep CTAs retire -- and
     // whose cloud copy is still in flight when the dependency wait ends -- are then the short column blocks.
@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
     unsigned ticket = 0u;
     auto loss_partial = [&](float mine) {
         double v = (double)mine;
+        __syncwarp();  // tells the compiler the warp is converged here: the shuffles below need no convergence wrappers
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) sRed[w] = v;
@@ -580,6 +581,7 @@ __global__ void __launch_bounds__(kFinThreads, 1024 / kFinThreads) chamfer_final
             double s1 = 0.0, s2 = 0.0;
             for (int q = lane; q < a.nrb; q += 32) s1 += lp[q];
             for (int q = lane; q < a.ncb; q += 32) s2 += lp[a.nrb + q];
+            __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 s1 += __shfl_down_sync(0xffffffffu, s1, o);

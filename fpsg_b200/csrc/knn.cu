@@ -669,7 +669,8 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     signed char* sCntP = reinterpret_cast<signed char*>(sThr + kSelQ);                // [T] candidates found by a thread, -1 = overflow
     signed char* sCnt = sCntP + kSelThreads;                                          // [Q] candidates of a query, -1 = overflow
 
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform (and with it every loop bound derived from it)
+    const int tid = threadIdx.x, lane = tid & 31, w = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int wq = w / kSelS, part = w - wq * kSelS;  // warps wq*4 .. wq*4+3 share 32 queries
     const int ql = wq * 32 + lane;                    // query of this thread inside the CTA
     const int b = blockIdx.y;
@@ -856,7 +857,9 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
             tq[z] = wq * 32 + part + (n + z) * kSelS;
             iq[z] = blockIdx.x * kSelQ + tq[z];
             if (iq[z] >= N) iq[z] = -1;  // warp-uniform
-            c[z] = iq[z] >= 0 ? sCnt[tq[z]] : 0;
+            // one value per warp (the same shared-memory word for all lanes); REDUX tells the compiler so: the loop bounds below are
+            // warp-uniform and the shuffles of the sorting networks need no convergence wrappers (174 of 349 had one)
+            c[z] = __reduce_max_sync(0xffffffffu, iq[z] >= 0 ? (int)sCnt[tq[z]] : 0);
             qp[z] = sTile[max(iq[z], 0)];
             key[z] = 0ull;
         }

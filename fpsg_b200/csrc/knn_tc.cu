@@ -789,7 +789,9 @@ knn_tc_rescore_kernel(const float* __restrict__ xt, const float* __restrict__ xx
                 j = (cursor - 1) * 32 + lane;
                 valid = ((word >> lane) & 1u) != 0u;
             }
+            __syncwarp();  // (also a hint: the warp is converged here, so the shuffles below need no convergence wrappers)
             u64 kb = score32(j, valid);
+            __syncwarp();
             kb = warp_sort_desc(kb, lane);
             if (first) {
                 key = kb;
