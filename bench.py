@@ -220,14 +220,15 @@ def secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M)
 
     # ---- c3: DGCNN kNN graph, k=20, B=32, N=1024: the xyz layer and the 64- / 128-channel layers (src/dgcnn/model.py:62-74)
     gk = torch.Generator(device="cpu").manual_seed(1234 + 3)
-    for C_ in (3, 64, 128):
-        xk = torch.randn(32, C_, 1024, generator=gk).to(dev)
-        ik = torch.empty(32, 1024, 20, dtype=torch.int64, device=dev)
-        nbk = L.fpsg_knn_workspace_bytes(32, C_, 1024, 20)
+    # (N = 1024 is BASELINE.json's c3; the reference's own clouds have 2048 points, src/datasets/modelnet.py: reported beside it)
+    for NK_, C_ in ((1024, 3), (1024, 64), (1024, 128), (2048, 3), (2048, 64), (2048, 128)):
+        xk = torch.randn(32, C_, NK_, generator=gk).to(dev)
+        ik = torch.empty(32, NK_, 20, dtype=torch.int64, device=dev)
+        nbk = L.fpsg_knn_workspace_bytes(32, C_, NK_, 20)
         wsk = torch.empty(max(nbk, 1), dtype=torch.uint8, device=dev)
-        us = _timed_us(torch, stream, dev, lambda: _lib.check(L.fpsg_knn_fwd(xk.data_ptr(), 32, C_, 1024, 20, ik.data_ptr(), wsk.data_ptr(), nbk, sp)), 20)
-        tf = (2 * C_ + 2) * 32 * 1024 * 1024 / us / 1e6
-        sec[f"c3_knn_k20_B32_N1024_C{C_}"] = {"us_per_call": us, "clouds_per_s": 32 / us * 1e6, "tflops": tf, "frac_of_fp32_peak": tf / fp32_peak_tflops,
+        us = _timed_us(torch, stream, dev, lambda: _lib.check(L.fpsg_knn_fwd(xk.data_ptr(), 32, C_, NK_, 20, ik.data_ptr(), wsk.data_ptr(), nbk, sp)), 20)
+        tf = (2 * C_ + 2) * 32 * NK_ * NK_ / us / 1e6
+        sec[("c3_" if NK_ == 1024 else "") + f"knn_k20_B32_N{NK_}_C{C_}"] = {"us_per_call": us, "clouds_per_s": 32 / us * 1e6, "tflops": tf, "frac_of_fp32_peak": tf / fp32_peak_tflops,
                                              "path": "FP32 threshold-selection kernel (knn.cu)" if C_ == 3 else
                                                      "tcgen05 FP16 pre-filter + exact FP32 re-scoring of the marked candidates (knn_tc.cu); tflops = the "
                                                      "algorithmic (2C+2) N^2 FLOP of the reference's matmul formulation over the time, not an FP32 rate"}
