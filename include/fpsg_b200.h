@@ -231,7 +231,13 @@ int fpsg_emd_sinkhorn_fwd(const float* p1, const float* p2, int B, int N, int M,
 /* ---- kNN graph ------------------------------------------------------------------------------------------ */
 /* x (B,C,N) channel-major FP32; idx (B,N,k) int64: the k nearest points of every point (self included),
  * nearest first, ranked by the reference's FP32 expression -|xi|^2 + 2 xi.xj - |xj|^2; equal values are
- * ordered by ascending index. 1 <= k <= min(N, FPSG_KNN_MAX_K). */
+ * ordered by ascending index. 1 <= k <= min(N, FPSG_KNN_MAX_K).
+ * Replaces `knn(x, k)`, src/dgcnn/model.py:13-20 (called at :28 for C = 3, 64, 64, 128). Three code paths, one result:
+ * C = 3 -- an FP32 threshold-selection kernel; C % 8 == 0, 16 <= C <= 128, k <= 32, 256 <= N <= 4096 (the DGCNN feature
+ * layers) -- a tensor-core pre-filter (tcgen05.mma on FP16 copies of the cloud, TMA-fed, TMEM accumulators) that marks a
+ * rigorous superset of the k nearest, followed by the exact FP32 expression on the marked candidates only; everything else
+ * -- FP32 list kernels. The workspace (fpsg_knn_workspace_bytes; 16-byte aligned) is scratch: no state survives the call.
+ * Non-finite features: the call terminates and every index is in [0, N); the ranking of NaN scores is unspecified. */
 #define FPSG_KNN_MAX_K 128
 size_t fpsg_knn_workspace_bytes(int B, int C, int N, int k);
 int fpsg_knn_fwd(const float* x, int B, int C, int N, int k, int64_t* idx, void* ws, size_t ws_bytes,
