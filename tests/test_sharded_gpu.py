@@ -75,3 +75,60 @@ def test_sharded_step_with_in_kernel_allreduce(lag):
     assert len(out) == world
     if world == 2:
         assert out[0] == out[1], "rank-ordered summation: the reduced values are bit-identical on every rank"
+
+
+def _pipeline_worker(rank, world, port, B, N, M, depth, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import fpsg_b200
+        from fpsg_b200.sharded import PeerScalarExchange, shard_range
+        from oracle import cpu_oracle as O
+        lo, hi = shard_range(B, rank, world)
+        pipe = fpsg_b200.ChamferPipeline(hi - lo, N, M, device=dev, depth=depth)
+        pipe.set_exchange(PeerScalarExchange(dev))
+        nb = 3 * depth + 2
+        batches = [make_pair(B, N, M, seed=700 + s) for s in range(nb)]
+        want_global = []
+        for p1, p2 in batches:
+            _, _, _, _, oloss = O.chamfer_fwd(p1.numpy(), p2.numpy())
+            want_global.append((float(oloss[lo:hi].astype(np.float64).sum()), float(oloss.astype(np.float64).sum())))
+        got_global = {}
+        nxt = done = 0
+        while done < nb:
+            while nxt < nb and pipe.in_flight < depth:
+                p1, p2 = batches[nxt]
+                if nxt % 2:
+                    pipe.submit(p1[lo:hi].contiguous(), p2[lo:hi].contiguous())
+                else:
+                    pipe.submit_device(p1[lo:hi].contiguous().to(dev), p2[lo:hi].contiguous().to(dev))
+                nxt += 1
+            s, _loss, _gp1 = pipe.result()
+            done += 1
+            assert abs(s - want_global[done - 1][0]) <= 1e-5 * abs(want_global[done - 1][0]), "local sum of the shard"
+            if done > depth:  # batch `done` collected the all-reduced sum of batch `done - depth`
+                got_global[done - depth] = pipe.previous_global_sum()
+        for n, g in got_global.items():
+            w = want_global[n - 1][1]
+            assert abs(g - w) <= 1e-5 * abs(w), (n, g, w)
+        out[rank] = [got_global[n] for n in sorted(got_global)]
+        pipe.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("depth", [1, 3, 4])
+def test_pipeline_lanes_with_in_kernel_allreduce(depth):
+    """The host-buffer pipeline with an exchange: every batch publishes its sum and collects that of batch n - depth (lag = the
+    number of lanes); host and device submits mixed."""
+    world = 2 if torch.cuda.device_count() >= 2 else 1
+    B, N, M = 6, 300, 257
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_pipeline_worker, args=(world, _free_port(), B, N, M, depth, out), nprocs=world, join=True)
+    assert len(out) == world
+    if world == 2:
+        assert out[0] == out[1], "rank-ordered summation: the reduced values are bit-identical on every rank"
