@@ -95,3 +95,28 @@ def test_knn_tensor_core_path_is_cuda_graph_capturable():
     graph.replay()  # and again: the workspace is reused without any re-initialisation by the host
     torch.cuda.synchronize()
     assert (idx.cpu().numpy() == O.knn_f32(x2.numpy(), k)).all()
+
+
+@pytest.mark.parametrize("B,C,N,k", [(2, 64, 1024, 20), (1, 128, 300, 20), (3, 16, 511, 7), (1, 72, 1100, 32), (1, 24, 2049, 5)])
+def test_knn_tensor_core_path_stays_inside_its_buffers(B, C, N, k):
+    """Guard zones around the workspace and the output (compute-sanitizer is not available on this pool): the four kernels of the
+    tensor-core path -- TMA stores into shared memory aside -- must not write a byte outside what the ABI hands them, and must not
+    depend on what the workspace held before."""
+    from fpsg_b200 import _lib
+    from oracle import cpu_oracle as O
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    G = 4096
+    x = make_cloud_cn(B, C, N, seed=3 * C + N).to(dev)
+    nb = int(L.fpsg_knn_workspace_bytes(B, C, N, k))
+    ws = torch.full((nb + 2 * G,), 0xA5, dtype=torch.uint8, device=dev)      # poisoned: stale workspace contents must not matter
+    out = torch.full((B * N * k + 2 * G // 8,), -7, dtype=torch.int64, device=dev)
+    ws_ptr, out_ptr = ws.data_ptr() + G, out.data_ptr() + G
+    assert ws_ptr % 16 == 0
+    for _ in range(2):
+        _lib.check(L.fpsg_knn_fwd(x.data_ptr(), B, C, N, k, out_ptr, ws_ptr, nb, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert bool((ws[:G] == 0xA5).all()) and bool((ws[G + nb:] == 0xA5).all()), "write outside the workspace"
+    assert bool((out[:G // 8] == -7).all()) and bool((out[G // 8 + B * N * k:] == -7).all()), "write outside the output"
+    got = out[G // 8:G // 8 + B * N * k].view(B, N, k).cpu().numpy()
+    assert (got == O.knn_f32(x.cpu().numpy(), k)).all()
