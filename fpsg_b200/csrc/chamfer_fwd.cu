@@ -139,6 +139,9 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R)) chamfer_s
     auto piece_units = [&](int cu_, int left_) { return min(min(kUps - (cu_ % kUps), a.ups - cu_), left_); };
 
     float px[R], py[R], pz[R], best[R];
+#ifdef FPSG_SWEEP_EXPANDED_PROBE
+    float an[R];  // |a|^2 (measurement-only build: the expanded form |a|^2 + |b|^2 - 2 a.b, NOT the reference's rounding)
+#endif
     int cur_bs = -1;                      // (pair, strip) whose rows are in registers
     int slot = 0, b = 0, strip = 0;
     float pf[kPf];    // the next piece's tile, in flight from global memory during the current piece
@@ -216,6 +219,10 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R)) chamfer_s
                     pz[k] = ok ? __ldg(rsrc + 3 * k + 2) : CUDART_INF_F;
                 }
             }
+#ifdef FPSG_SWEEP_EXPANDED_PROBE
+#pragma unroll
+            for (int k = 0; k < R; ++k) an[k] = __fmaf_rn(px[k], px[k], __fmaf_rn(py[k], py[k], __fmul_rn(pz[k], pz[k])));
+#endif
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 best[k] = CUDART_INF_F;
@@ -242,6 +249,29 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R)) chamfer_s
             const float4 v1 = *reinterpret_cast<const float4*>(tile + 12 * step + 4);  // y1 z1 x2 y2
             const float4 v2 = *reinterpret_cast<const float4*>(tile + 12 * step + 8);  // z2 x3 y3 z3
             float c0m = CUDART_INF_F, c1m = CUDART_INF_F, c2m = CUDART_INF_F, c3m = CUDART_INF_F;
+#ifdef FPSG_SWEEP_EXPANDED_PROBE
+            // per column (-2x, -2y, -2z, |b|^2): in a real filter kernel the tile would hold these (computed once per tile by one
+            // lane); here every thread derives them per step (24 operations per 64 evaluations: the probe is pessimistic by that)
+            const float q0x = -2.f * v0.x, q0y = -2.f * v0.y, q0z = -2.f * v0.z, q0n = __fmaf_rn(v0.x, v0.x, __fmaf_rn(v0.y, v0.y, v0.z * v0.z));
+            const float q1x = -2.f * v0.w, q1y = -2.f * v1.x, q1z = -2.f * v1.y, q1n = __fmaf_rn(v0.w, v0.w, __fmaf_rn(v1.x, v1.x, v1.y * v1.y));
+            const float q2x = -2.f * v1.z, q2y = -2.f * v1.w, q2z = -2.f * v2.x, q2n = __fmaf_rn(v1.z, v1.z, __fmaf_rn(v1.w, v1.w, v2.x * v2.x));
+            const float q3x = -2.f * v2.y, q3y = -2.f * v2.z, q3z = -2.f * v2.w, q3n = __fmaf_rn(v2.y, v2.y, __fmaf_rn(v2.z, v2.z, v2.w * v2.w));
+#define FPSG_EXPD(k_, qx, qy, qz, qn) __fmaf_rn(px[k_], qx, __fmaf_rn(py[k_], qy, __fmaf_rn(pz[k_], qz, __fadd_rn(qn, an[k_]))))
+#pragma unroll
+            for (int k = 0; k < R; k += 2) {
+                const float a0 = FPSG_EXPD(k, q0x, q0y, q0z, q0n), a1 = FPSG_EXPD(k, q1x, q1y, q1z, q1n);
+                const float a2 = FPSG_EXPD(k, q2x, q2y, q2z, q2n), a3 = FPSG_EXPD(k, q3x, q3y, q3z, q3n);
+                const float b0 = FPSG_EXPD(k + 1, q0x, q0y, q0z, q0n), b1 = FPSG_EXPD(k + 1, q1x, q1y, q1z, q1n);
+                const float b2 = FPSG_EXPD(k + 1, q2x, q2y, q2z, q2n), b3 = FPSG_EXPD(k + 1, q3x, q3y, q3z, q3n);
+                best[k] = min3(min3(best[k], a0, a1), a2, a3);
+                best[k + 1] = min3(min3(best[k + 1], b0, b1), b2, b3);
+                c0m = min3(c0m, a0, b0);
+                c1m = min3(c1m, a1, b1);
+                c2m = min3(c2m, a2, b2);
+                c3m = min3(c3m, a3, b3);
+            }
+#undef FPSG_EXPD
+#else
 #pragma unroll
             for (int k = 0; k < R; k += 2) {
                 const float a0 = sqdist(px[k], py[k], pz[k], v0.x, v0.y, v0.z);
@@ -259,6 +289,7 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R)) chamfer_s
                 c2m = min3(c2m, a2, b2);
                 c3m = min3(c3m, a3, b3);
             }
+#endif
             // column direction: warp minimum + the lanes that attain it, one 8-byte record per column
             const float m0 = warp_min_f32(c0m), m1 = warp_min_f32(c1m), m2 = warp_min_f32(c2m), m3 = warp_min_f32(c3m);
             const unsigned h0 = __ballot_sync(0xffffffffu, c0m == m0);

@@ -14,7 +14,12 @@ constexpr int kSub = 32;   // columns per shared-memory sub-block (2 units)
 static_assert(kSub == 32, "the arg-min recovery permutes a row's window with lane ^ c");
 
 // resident sweep CTAs per SM (register-limited): the persistent grid is this times the SM count
+#ifdef FPSG_SWEEP_EXPANDED_PROBE
+// measurement-only build (bench_micro/expanded_probe.py): 16 more registers per thread for |a|^2 -> three CTAs per SM
+constexpr int sweep_ctas_per_sm(int R) { return R >= 16 ? FPSG_SWEEP_EXPANDED_PROBE : 6; }
+#else
 constexpr int sweep_ctas_per_sm(int R) { return R >= 16 ? 4 : 6; }
+#endif
 
 struct ChamferPlan {
     int R;            // rows per thread in the sweep
