@@ -620,12 +620,17 @@ def main():
             if e2e_exchange is not None and i >= 1 and (i & 63) == 0:
                 acc += 0.0 * pipe.previous_global_sum()  # the all-reduced loss of the previous step, as a logger would read it
         return acc
-    e2e_loop(10)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(e2e_steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    # The loop is host-driven and one pass lasts only ~45 ms: three passes, the median is reported and all three are listed
+    # (a single pass right after the other sections of this script varied between 0.56 and 0.73 M pairs/s from run to run)
+    e2e_loop(200)
+    e2e_reps = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(e2e_steps)
+        barrier()
+        e2e_reps.append(time.perf_counter() - t0)
+    e2e_s = sorted(e2e_reps)[1]
     pipe.close()
 
     # ---- end to end through the reference-facing Python call with autograd: kaolin shim chamfer_distance(p1, p2).sum()
@@ -687,7 +692,7 @@ def main():
                        "lanes": LANES,
                        "parity": "Chamfer oracle is parity-unpinned (Kaolin 0.9.0 absent): bit-exact vs the restated algorithm; kNN and input pipeline pinned"},
             "e2e": {"value": pairs * e2e_steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": (2 + B) * 4,
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "passes_pairs_per_s": [pairs * e2e_steps / t_ for t_ in e2e_reps], "reported": "median of three passes",
                     "api": "fpsg_chamfer_pipeline_submit / _result (include/fpsg_b200.h; fpsg_b200.ChamferPipeline): every step copies its own inputs "
                            "from pinned HOST memory, runs sweep + finish and reads its per-pair losses and their sum back to the host; depth 4, so the "
                            "H2D copies of step i+1 overlap the kernels of step i; the gradient stays on the device as in the reference"},

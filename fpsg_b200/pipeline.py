@@ -38,6 +38,7 @@ class ChamferPipeline:
         self._sum = ctypes.c_float()
         self._gp = ctypes.c_void_p()
         self._base = self._arena.data_ptr()
+        self._gp_views = {}
 
     def set_exchange(self, exchange) -> None:
         """Multi-GPU: every batch takes part in the in-kernel scalar all-reduce (``fpsg_b200.sharded.PeerScalarExchange``,
@@ -74,7 +75,9 @@ class ChamferPipeline:
         _lib.check(_lib.lib().fpsg_chamfer_pipeline_result(self._h, ctypes.byref(self._sum), self._loss.data_ptr(), ctypes.byref(self._gp), None, None))
         self._keep.pop(0)
         off = self._gp.value - self._base
-        gp1 = self._arena[off:off + self.B * self.N * 12].view(torch.float32).view(self.B, self.N, 3)
+        gp1 = self._gp_views.get(off)
+        if gp1 is None:  # one view per slot, built once: the call is on the per-step host path
+            gp1 = self._gp_views[off] = self._arena[off:off + self.B * self.N * 12].view(torch.float32).view(self.B, self.N, 3)
         return self._sum.value, self._loss, gp1
 
     @property
