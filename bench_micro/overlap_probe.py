@@ -6,7 +6,9 @@ Usage: overlap_probe.py [B N M]"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from fpsg_b200 import _lib
+from fpsg_b200 import _lib, build
+if os.environ.get("FPSG_TUNING_LIB"):   # the development build, so that the FPSG_* switches take effect
+    _lib.use_library(build.LIB_TUNING)
 from bench import make_inputs
 
 L = _lib.lib()
@@ -57,7 +59,7 @@ def run(ns, it):
     return e0.elapsed_time(e1) / it * 1e3
 
 
-res = {"B": B, "N": N, "M": M}
+res = {"B": B, "N": N, "M": M, "env": {k: v for k, v in os.environ.items() if k.startswith("FPSG_")}}
 it = 600 if B * N * M < 5e9 else 30
 for ns in (1, 2, 3, 4):
     run(ns, 40)

@@ -62,7 +62,7 @@ struct FinishArgs {
 };
 
 struct FinishSmem {
-    size_t p2, p1, cnt1, bkt1, ovf1, cnt2, bkt2, ovf2, misc, loss, total;
+    size_t p2, p1, cnt1, bkt1, ovf1, cnt2, bkt2, ovf2, head1, head2, misc, loss, total;
 };
 
 static FinishSmem finish_smem_layout(int N, int M, int rpcN, int rpcM, bool want2, int nwarps) {
@@ -85,6 +85,10 @@ static FinishSmem finish_smem_layout(int N, int M, int rpcN, int rpcM, bool want
     if (want2) off += align_up((size_t)rpcM * kBucket * 2, 16);
     L.ovf2 = off;
     if (want2) off += align_up((size_t)N * 4, 16);
+    L.head1 = off;  // per point: head of its chain in the overflow list (0xFFFF = none)
+    off += align_up((size_t)rpcN * 4, 16);
+    L.head2 = off;
+    if (want2) off += align_up((size_t)rpcM * 4, 16);
     L.misc = off;  // [0] overflow count side 1, [1] overflow count side 2
     off += 16;
     L.loss = off;  // [cluster rank][warp][2] doubles (used in rank 0)
@@ -94,7 +98,7 @@ static FinishSmem finish_smem_layout(int N, int M, int rpcN, int rpcM, bool want
 }
 
 struct FinishSmemOff {
-    unsigned p2, p1, cnt1, bkt1, ovf1, cnt2, bkt2, ovf2, misc, loss;
+    unsigned p2, p1, cnt1, bkt1, ovf1, cnt2, bkt2, ovf2, head1, head2, misc, loss;
 };
 
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -111,6 +115,8 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishClusterMax + 64, 2) 
     unsigned* sCnt2 = reinterpret_cast<unsigned*>(smem + so.cnt2);
     unsigned short* sBkt2 = reinterpret_cast<unsigned short*>(smem + so.bkt2);
     unsigned* sOvf2 = reinterpret_cast<unsigned*>(smem + so.ovf2);
+    unsigned* sHead1 = reinterpret_cast<unsigned*>(smem + so.head1);
+    unsigned* sHead2 = reinterpret_cast<unsigned*>(smem + so.head2);
     unsigned* sMisc = reinterpret_cast<unsigned*>(smem + so.misc);
     double* sLoss = reinterpret_cast<double*>(smem + so.loss);
 
@@ -151,9 +157,15 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishClusterMax + 64, 2) 
         for (int q = f2 + tid; q < 3 * a.M32; q += nthreads) sP2[q] = CUDART_INF_F;
         for (int q = 4 * v1 + tid; q < f1; q += nthreads) sP1[q] = __ldg(p1b + q);
         for (int q = f1 + tid; q < 3 * a.N32; q += nthreads) sP1[q] = CUDART_INF_F;
-        for (int q = tid; q < a.rpcN; q += nthreads) sCnt1[q] = 0u;
+        for (int q = tid; q < a.rpcN; q += nthreads) {
+            sCnt1[q] = 0u;
+            sHead1[q] = 0xffffu;
+        }
         if (kWant2)
-            for (int q = tid; q < a.rpcM; q += nthreads) sCnt2[q] = 0u;
+            for (int q = tid; q < a.rpcM; q += nthreads) {
+                sCnt2[q] = 0u;
+                sHead2[q] = 0xffffu;
+            }
         if (tid < 4) sMisc[tid] = 0u;
     }
     cluster_arrive_release();  // barrier #1 (split): this CTA's counters are zero; waited for just before the pushes
@@ -289,8 +301,10 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishClusterMax + 64, 2) 
         if (pos < (unsigned)kBucket)
             cluster.map_shared_rank(sBkt1, ro)[loc * kBucket + pos] = (unsigned short)j;
         else {
+            // a longer bucket continues as a chain through the owner's overflow list: entry = (previous head << 16) | j
             const unsigned o = atomicAdd(cluster.map_shared_rank(sMisc, ro), 1u);
-            cluster.map_shared_rank(sOvf1, ro)[o] = ((unsigned)loc << 16) | (unsigned)j;
+            const unsigned prev = atomicExch(cluster.map_shared_rank(sHead1, ro) + loc, o);
+            cluster.map_shared_rank(sOvf1, ro)[o] = (prev << 16) | (unsigned)j;
         }
     }
     if (kWant2 && rvalid && gp2b) {
@@ -300,7 +314,8 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishClusterMax + 64, 2) 
             cluster.map_shared_rank(sBkt2, ro)[loc * kBucket + pos] = (unsigned short)i;
         else {
             const unsigned o = atomicAdd(cluster.map_shared_rank(sMisc, ro) + 1, 1u);
-            cluster.map_shared_rank(sOvf2, ro)[o] = ((unsigned)loc << 16) | (unsigned)i;
+            const unsigned prev = atomicExch(cluster.map_shared_rank(sHead2, ro) + loc, o);
+            cluster.map_shared_rank(sOvf2, ro)[o] = (prev << 16) | (unsigned)i;
         }
     }
     cluster_arrive_release();  // barrier #2: buckets and loss partials of the whole pair are complete
@@ -349,16 +364,15 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishClusterMax + 64, 2) 
                 }
             }
         }
-        if (__any_sync(0xffffffffu, c > (unsigned)kBucket)) {  // a hub in this warp: its spilled edges are in the CTA's overflow list
-            const unsigned n = sMisc[0];
-            for (unsigned o = 0; o < n; ++o) {
+        if (c > (unsigned)kBucket) {  // a hub: the rest of its bucket is a chain in the CTA's overflow list (only this thread walks it;
+                                      // scanning the whole list per thread was a fifth of the kernel's instructions on the bench's clouds)
+            for (unsigned o = sHead1[tid]; o != 0xffffu;) {
                 const unsigned v = sOvf1[o];
-                if ((v >> 16) == (unsigned)tid) {
-                    const float* s = sP2 + 3 * (v & 0xffffu);
-                    gx += (double)__fmul_rn(u2, __fsub_rn(ax, s[0]));
-                    gy += (double)__fmul_rn(u2, __fsub_rn(ay, s[1]));
-                    gz += (double)__fmul_rn(u2, __fsub_rn(az, s[2]));
-                }
+                const float* s = sP2 + 3 * (v & 0xffffu);
+                gx += (double)__fmul_rn(u2, __fsub_rn(ax, s[0]));
+                gy += (double)__fmul_rn(u2, __fsub_rn(ay, s[1]));
+                gz += (double)__fmul_rn(u2, __fsub_rn(az, s[2]));
+                o = v >> 16;
             }
         }
         if (rvalid) {
@@ -388,16 +402,14 @@ __global__ void __launch_bounds__(kFinishMaxPoints / kFinishClusterMax + 64, 2) 
                 }
             }
         }
-        if (__any_sync(0xffffffffu, c > (unsigned)kBucket)) {
-            const unsigned n = sMisc[1];
-            for (unsigned o = 0; o < n; ++o) {
+        if (c > (unsigned)kBucket) {
+            for (unsigned o = sHead2[tid]; o != 0xffffu;) {
                 const unsigned v = sOvf2[o];
-                if ((v >> 16) == (unsigned)tid) {
-                    const float* s = sP1 + 3 * (v & 0xffffu);
-                    gx += (double)__fmul_rn(u1, __fsub_rn(qx, s[0]));
-                    gy += (double)__fmul_rn(u1, __fsub_rn(qy, s[1]));
-                    gz += (double)__fmul_rn(u1, __fsub_rn(qz, s[2]));
-                }
+                const float* s = sP1 + 3 * (v & 0xffffu);
+                gx += (double)__fmul_rn(u1, __fsub_rn(qx, s[0]));
+                gy += (double)__fmul_rn(u1, __fsub_rn(qy, s[1]));
+                gz += (double)__fmul_rn(u1, __fsub_rn(qz, s[2]));
+                o = v >> 16;
             }
         }
         if (cvalid) {
@@ -474,7 +486,7 @@ int chamfer_finish_launch(const SegTable& seg, const ChamferPlan& pl, int B, int
     const int threads = fa.rpcN > fa.rpcM ? fa.rpcN : fa.rpcM;
     const FinishSmem L = finish_smem_layout(N, M, fa.rpcN, fa.rpcM, want2, threads / 32);
     const FinishSmemOff so{(unsigned)L.p2, (unsigned)L.p1, (unsigned)L.cnt1, (unsigned)L.bkt1, (unsigned)L.ovf1, (unsigned)L.cnt2, (unsigned)L.bkt2,
-                           (unsigned)L.ovf2, (unsigned)L.misc, (unsigned)L.loss};
+                           (unsigned)L.ovf2, (unsigned)L.head1, (unsigned)L.head2, (unsigned)L.misc, (unsigned)L.loss};
     auto kern = want2 ? chamfer_finish_kernel<true> : chamfer_finish_kernel<false>;
     size_t smem_req = L.total;
     bool one_per_sm = false;
@@ -489,7 +501,7 @@ int chamfer_finish_launch(const SegTable& seg, const ChamferPlan& pl, int B, int
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = tune_env("FPSG_FIN_NOPDL") ? 0 : 1;  // (tuning build: plain stream order)
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = kFinishCluster;
     attr[1].val.clusterDim.y = 1;

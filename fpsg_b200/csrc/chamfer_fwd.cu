@@ -693,7 +693,10 @@ int chamfer_sweep_launch(const SegTable& seg, const ChamferPlan& pl, int B, int 
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
     }
-    if (pl.R == 16)
+    if (pl.R == 16 && tune_env("FPSG_SWEEP_NOPDL")) {  // tuning build: plain stream order (the grid starts when its predecessor has finished)
+        chamfer_sweep_kernel<16><<<sgrid, sblock, 0, stream>>>(sa);
+        FPSG_CUDA_OK(cudaGetLastError());
+    } else if (pl.R == 16)
         FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<16>, sgrid, sblock, 0, stream, sa));
     else if (pl.R == 8)
         FPSG_CUDA_OK(launch_pdl(chamfer_sweep_kernel<8>, sgrid, sblock, 0, stream, sa));
