@@ -19,7 +19,7 @@ sets = max(4, min(96, int(160e6 / (B * (N + M) * 12))))
 ring = [make_inputs(B, N, M, seed=1235 + s, device=dev) for s in range(sets)]
 ptrs = [(a.data_ptr(), b.data_ptr()) for a, b in ring]
 nb = L.fpsg_chamfer_fwd_workspace_bytes(B, N, M)
-MAXS = 4
+MAXS = 8
 
 
 class Slot:
@@ -61,7 +61,7 @@ def run(ns, it):
 
 res = {"B": B, "N": N, "M": M, "env": {k: v for k, v in os.environ.items() if k.startswith("FPSG_")}}
 it = 600 if B * N * M < 5e9 else 30
-for ns in (1, 2, 3, 4):
+for ns in (1, 2, 3, 4, 6, 8):
     run(ns, 40)
     res[f"streams{ns}_us_per_step"] = round(min(run(ns, it) for _ in range(3)), 2)
 
