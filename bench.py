@@ -617,15 +617,17 @@ def main():
 
     # ---- end to end, headline: the host-buffer call of the C ABI (fpsg_chamfer_pipeline_*, fpsg_b200.ChamferPipeline): every
     # step copies ITS inputs from pinned host memory (H2D, 1.57 MB), runs the fused loss step and reads its losses back
-    # (D2H); up to 4 steps are in flight (one lane each), so the copies of step i+1 overlap the kernels of step i ----
+    # (D2H); up to DEPTH steps are in flight (one lane each), so the copies of step i+1 overlap the kernels of step i ----
     host = []
     for s_ in range(8):
         h1, h2 = make_inputs(B, N, M, seed=777 + 1000 * rank + s_, pin=True)
         host.append((h1, h2))
-    DEPTH = int(os.environ.get("FPSG_BENCH_DEPTH", "4"))  # = lanes of the pipeline (measured: 261 / 494 / 640 / 715 / 732 k pairs/s at depth 1 / 2 / 3 / 4 / 6, profiles/r02b_e2e_depth.json)
+    DEPTH = int(os.environ.get("FPSG_BENCH_DEPTH", "6"))  # steps in flight INCLUDING those whose host->device copy is still running: four in the kernels + two copying
+    # (measured: 261 / 494 / 640 / 715 / 732 k pairs/s at depth 1 / 2 / 3 / 4 / 6, profiles/r02b_e2e_depth.json; depth 4 varies 450-735 k from run to run, depth 6 737-750 k:
+    # profiles/r02d_e2e_trigger.jsonl)
     pipe = fpsg_b200.ChamferPipeline(B, N, M, device=dev, depth=DEPTH)
     e2e_exchange = None
-    if exchange is not None:  # N > 1: every step of the pipeline takes part in the in-kernel scalar all-reduce (lag 1)
+    if exchange is not None:  # N > 1: every step of the pipeline takes part in the in-kernel scalar all-reduce (lag = DEPTH)
         from fpsg_b200.sharded import PeerScalarExchange
         e2e_exchange = PeerScalarExchange(dev)
         pipe.set_exchange(e2e_exchange)
@@ -714,10 +716,10 @@ def main():
                                  f"value_single_stream / latency_us_per_step = the same steps strictly one after the other on one stream",
                        "lanes": LANES,
                        "parity": "Chamfer oracle is parity-unpinned (Kaolin 0.9.0 absent): bit-exact vs the restated algorithm; kNN and input pipeline pinned"},
-            "e2e": {"value": pairs * e2e_steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": (2 + B) * 4,
+            "e2e": {"value": pairs * e2e_steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": (2 + B + _lib.PEER_RING) * 4,
                     "steps": e2e_steps, "passes_pairs_per_s": [pairs * e2e_steps / t_ for t_ in e2e_reps], "reported": "median of three passes",
                     "api": "fpsg_chamfer_pipeline_submit / _result (include/fpsg_b200.h; fpsg_b200.ChamferPipeline): every step copies its own inputs "
-                           "from pinned HOST memory, runs sweep + finish and reads its per-pair losses and their sum back to the host; depth 4, so the "
+                           "from pinned HOST memory, runs sweep + finish and reads its per-pair losses and their sum back to the host (with the ring of all-reduced sums); depth " + str(DEPTH) + ", so the "
                            "H2D copies of step i+1 overlap the kernels of step i; the gradient stays on the device as in the reference"},
             "e2e_autograd": {"value": pairs * ag_steps / ag_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": 4,
                              "steps": ag_steps,

@@ -32,7 +32,7 @@ class ChamferSegment(ctypes.Structure):
 
 
 MAX_PEERS = 8
-PEER_RING = 16
+PEER_RING = 32
 
 
 class PeerExchange(ctypes.Structure):

@@ -164,7 +164,11 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R)) chamfer_s
     // polls the progress words (chamfer_finish.cu) can never see a stale value of an earlier launch.
     __threadfence();
     __syncthreads();
-    cudaTriggerProgrammaticLaunchCompletion();
+    bool triggered = false;
+    if (left <= a.trig_left) {
+        cudaTriggerProgrammaticLaunchCompletion();
+        triggered = true;
+    }
 
     auto fetch = [&](int bs_, int cu_, int n_) {  // global -> registers; INF beyond the piece: padded columns never win
         const int b_ = a.strips == 1 ? bs_ : bs_ / a.strips;
@@ -178,6 +182,10 @@ __global__ void __launch_bounds__(kSweepThreads, sweep_ctas_per_sm(R)) chamfer_s
     if (left > 0) fetch(bs, cu, piece_units(cu, left));
 
     while (left > 0) {
+        if (!triggered && left <= a.trig_left) {  // (CTA-uniform) a later trigger keeps the dependent grid's CTAs off the SMs for longer
+            cudaTriggerProgrammaticLaunchCompletion();
+            triggered = true;
+        }
         const int nun = piece_units(cu, left);
         const int cbeg = cu * kUnit;
         const int cend = min(a.M, cbeg + nun * kUnit);
@@ -671,12 +679,24 @@ int chamfer_prepare(const SegTable& seg, int B, int N, int M, void* ws, size_t w
     return FPSG_OK;
 }
 
+// units left in a CTA's run when it lets the next grid of the chain launch (see SweepArgs::trig_left)
+static int sweep_trigger_left(const ChamferPlan& pl) {
+    // Percent of the run still to do at the trigger. 100 = right at the start: the dependent grid's CTAs (finish / finalize) then
+    // become resident as soon as the first sweep CTAs retire and wait on the SMs for their pair, in slots that the sweep of the
+    // NEXT step (issued on another lane) could use. 60: they arrive when all sweep CTAs are 40 % through -- still well ahead of
+    // the first completed pair (one step alone: 53.4 us either way), and four or more lanes gain 1.2 us per step (43.7 -> 42.4;
+    // two lanes lose 2 us: profiles/r02d_trigger_variants.jsonl).
+    int pct = 60;
+    if (const char* e = tune_env("FPSG_SWEEP_TRIGGER_PCT")) pct = atoi(e);  // tuning build only
+    return pct >= 100 ? 0x7fffffff : (int)((long long)(pl.q + 1) * pct / 100);
+}
+
 int chamfer_sweep_launch(const SegTable& seg, const ChamferPlan& pl, int B, int N, int M, void* ws, cudaStream_t stream) {
     char* base = static_cast<char*>(ws);
     const SweepArgs sa{seg, N, M, pl.strips, pl.ups, pl.q, pl.r, pl.maxslots, pl.Mpad, reinterpret_cast<float*>(base + pl.rowmin_off),
                        reinterpret_cast<int*>(base + pl.rowsub_off), reinterpret_cast<u64*>(base + pl.colpart_off),
                        reinterpret_cast<unsigned*>(base + pl.counters_off), B, reinterpret_cast<unsigned*>(base + pl.progress_off),
-                       trace_buffer()};
+                       trace_buffer(), sweep_trigger_left(pl)};
     const dim3 sgrid((unsigned)pl.grid), sblock(kSweepThreads);
     // Shared-memory carve-out: the sweep itself needs 76 KB per SM, for which the driver would configure 100 KB -- and the
     // kernel that follows it in the chain (finalize / finish: 25-60 KB per CTA, staged ahead of its dependency wait) could

@@ -59,6 +59,8 @@ struct SweepArgs {
     int B;
     unsigned* progress;         // [grid] see above
     unsigned long long* trace;  // timeline stamps (tuning builds), else nullptr
+    int trig_left;              // the launch-completion trigger is executed once at most this many units of the run are left
+                                // (>= the run length: right away, after the progress word was zeroed)
 };
 
 // Scalar all-reduce through peer memory (multi-GPU, one process per GPU; include/fpsg_b200.h fpsg_peer_exchange_t): every

@@ -14,12 +14,12 @@ from . import _lib
 
 
 class ChamferPipeline:
-    """``pipe = ChamferPipeline(B, N, M, device=..., depth=3)``; per batch ``pipe.submit(p1_cpu, p2_cpu)`` then, possibly
+    """``pipe = ChamferPipeline(B, N, M, device=..., depth=4)``; per batch ``pipe.submit(p1_cpu, p2_cpu)`` then, possibly
     after further submits, ``loss_sum, loss, gp1 = pipe.result()``: the sum over the batch of
     ``w1*mean(dist1) + w2*mean(dist2)`` (a Python float), the per-pair losses (CPU tensor (B,)), and the gradient of the
     sum w.r.t. p1 as a CUDA tensor (B,N,3) that aliases the pipeline's arena (valid until ``depth`` further submits)."""
 
-    def __init__(self, B: int, N: int, M: int, device=None, w1: float = 1.0, w2: float = 1.0, depth: int = 3):
+    def __init__(self, B: int, N: int, M: int, device=None, w1: float = 1.0, w2: float = 1.0, depth: int = 4):
         L = _lib.lib()
         self.B, self.N, self.M, self.depth = int(B), int(N), int(M), int(depth)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

@@ -142,7 +142,7 @@ int fpsg_chamfer_multi_loss_fwd_bwd(const fpsg_chamfer_segment_t* segs_host, int
  * global_out (FPSG_PEER_RING floats, device): global_out[(seq - lag) % FPSG_PEER_RING] = sum over the ranks, added
  * in rank order (bit-identical on every rank). Pass px = NULL for a single-GPU step. */
 #define FPSG_MAX_PEERS 8
-#define FPSG_PEER_RING 16
+#define FPSG_PEER_RING 32
 typedef struct fpsg_peer_exchange {
     unsigned long long* table[FPSG_MAX_PEERS];
     float* global_out;

@@ -35,7 +35,7 @@ def _worker(rank, world, port, B, N, M, lag, out):
         lo, hi = shard_range(B, rank, world)
         step = ShardedChamferStep(hi - lo, N, M, dev, lag=lag)
         res = []
-        for it in range(19):  # more steps than the ring has slots
+        for it in range(37):  # more steps than the ring has slots (32)
             p1, p2 = make_pair(B, N, M, seed=500 + it)
             a, b = p1[lo:hi].contiguous().to(dev), p2[lo:hi].contiguous().to(dev)
             loss, local_sum, gp1, seq = step(a, b)
@@ -65,7 +65,7 @@ def _worker(rank, world, port, B, N, M, lag, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("lag", [0, 1, 3])
+@pytest.mark.parametrize("lag", [0, 1, 3, 8])
 def test_sharded_step_with_in_kernel_allreduce(lag):
     world = 2 if torch.cuda.device_count() >= 2 else 1
     B, N, M = 6, 300, 257
@@ -90,7 +90,7 @@ def _pipeline_worker(rank, world, port, B, N, M, depth, out):
         lo, hi = shard_range(B, rank, world)
         pipe = fpsg_b200.ChamferPipeline(hi - lo, N, M, device=dev, depth=depth)
         pipe.set_exchange(PeerScalarExchange(dev))
-        nb = 3 * depth + 2
+        nb = max(3 * depth + 2, 35)  # wraps the ring of 32 slots
         batches = [make_pair(B, N, M, seed=700 + s) for s in range(nb)]
         want_global = []
         for p1, p2 in batches:
@@ -120,7 +120,7 @@ def _pipeline_worker(rank, world, port, B, N, M, depth, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("depth", [1, 3, 4])
+@pytest.mark.parametrize("depth", [1, 3, 4, 8])
 def test_pipeline_lanes_with_in_kernel_allreduce(depth):
     """The host-buffer pipeline with an exchange: every batch publishes its sum and collects that of batch n - depth (lag = the
     number of lanes); host and device submits mixed."""
