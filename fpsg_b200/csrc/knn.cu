@@ -593,7 +593,8 @@ knn_gemm_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
 constexpr int kSelS = 4;                        // warps that share 32 queries in pass 1
 constexpr int kSelThreads = 256;
 constexpr int kSelQ = kSelThreads / kSelS;      // queries per CTA
-constexpr int kSelGroups = 32;                  // coarse groups (>= k)
+constexpr int kSelGroups = 64;                  // coarse groups (>= k): their k-th largest maximum is the threshold
+constexpr int kSelGpp = kSelGroups / kSelS;     // coarse groups per part (sorted in that thread's registers)
 constexpr int kSelFine = 128;                   // most fine groups per cloud
 constexpr int kSelFmStride = kSelFine + 2;      // 16-bit elements per query row of the fine maxima (65 words: conflict-free)
 constexpr int kSelCap = 64;                     // candidates per query
@@ -608,6 +609,50 @@ __device__ __forceinline__ float knn_pd3(const float4 q, const float xxi, const 
     return __fsub_rn(__fmaf_rn(2.0f, dot, c.w), xxi);
 }
 
+
+// rn(2 dot - xx_j): pd before the query's own norm is subtracted. x -> rn(x - xx_i) is monotone, so maxima may be taken on this
+// value and the subtraction applied once per group (same bits as the maximum of the pd values; NaN paddings are ignored by max)
+__device__ __forceinline__ float knn_t3(const float4 q, const float4 c) {
+    float dot = __fmul_rn(q.x, c.x);
+    dot = __fmaf_rn(q.y, c.y, dot);
+    dot = __fmaf_rn(q.z, c.z, dot);
+    return __fmaf_rn(2.0f, dot, c.w);
+}
+
+// bitonic networks on a thread's registers (fully unrolled: static indices only)
+template <int NV>
+__device__ __forceinline__ void regs_merge_desc(float (&v)[NV]) {  // bitonic sequence -> descending
+#pragma unroll
+    for (int d = NV >> 1; d > 0; d >>= 1) {
+#pragma unroll
+        for (int e = 0; e < NV; ++e) {
+            if ((e & d) == 0) {
+                const float hi = fmaxf(v[e], v[e | d]), lo = fminf(v[e], v[e | d]);
+                v[e] = hi;
+                v[e | d] = lo;
+            }
+        }
+    }
+}
+template <int NV>
+__device__ __forceinline__ void regs_sort_desc(float (&v)[NV]) {
+#pragma unroll
+    for (int s = 2; s <= NV; s <<= 1) {
+#pragma unroll
+        for (int d = s >> 1; d > 0; d >>= 1) {
+#pragma unroll
+            for (int e = 0; e < NV; ++e) {
+                const int p = e ^ d;
+                if (p > e) {
+                    const bool desc = (s == NV) || ((e & s) == 0);
+                    const float hi = fmaxf(v[e], v[p]), lo = fminf(v[e], v[p]);
+                    v[e] = desc ? hi : lo;
+                    v[p] = desc ? lo : hi;
+                }
+            }
+        }
+    }
+}
 
 // sorts two independent key sets at once (the two shuffle chains overlap: the stage is latency-bound otherwise)
 __device__ __forceinline__ void warp_sort_desc2(u64& a, u64& b, int lane) {
@@ -638,9 +683,10 @@ struct KnnSelPlan {
 };
 constexpr size_t kSelRegionA = (size_t)kSelColCap * kSelThreads * sizeof(unsigned short);  // fine maxima, later the candidate columns
 constexpr size_t kSelRegionB = (size_t)kSelQ * kSelListStride * sizeof(unsigned short);    // coarse maxima, group lists, query lists
-static_assert(kSelRegionA >= (size_t)kSelQ * kSelFmStride * sizeof(unsigned short), "fine maxima fit the candidate-column region");
-static_assert(kSelRegionB >= (size_t)kSelGroups * kSelQ * sizeof(float) && kSelRegionB >= (size_t)(kSelFine / kSelS) * kSelThreads,
-              "region B holds the sorted group maxima and the per-thread group lists");
+constexpr size_t kSelFmBytes = (size_t)kSelQ * kSelFmStride * sizeof(unsigned short);         // fine maxima, at the head of region A
+static_assert(kSelFmBytes % 16 == 0 && kSelFmBytes + (size_t)kSelGroups * kSelQ * sizeof(float) <= kSelRegionA + kSelRegionB,
+              "the exact coarse maxima ([64][Q] floats) fit behind the fine maxima: the tail of region A and all of region B");
+static_assert(kSelRegionB >= (size_t)(kSelFine / kSelS) * kSelThreads, "region B holds the per-thread group lists");
 static KnnSelPlan knn_select_plan(int N) {
     KnnSelPlan p;
     p.fsh = 3;
@@ -662,7 +708,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     unsigned char* regB = regA + kSelRegionA;
     unsigned short* sFm = reinterpret_cast<unsigned short*>(regA);                    // [Q][130] fine group maxima, rounded UP to 16 bits ...
     unsigned short* sBuf = reinterpret_cast<unsigned short*>(regA);                   // ... then [48][T] candidate columns
-    float* sScr = reinterpret_cast<float*>(regB);                                     // [32][Q] exact coarse maxima (then sorted) ...
+    float* sScr = reinterpret_cast<float*>(regA + kSelFmBytes);                       // [64][Q] exact coarse maxima (then sorted): tail of A + B ...
     unsigned char* sGl = regB;                                                        // ... then [32][T] fine groups to re-score ...
     unsigned short* sList = reinterpret_cast<unsigned short*>(regB);                  // ... then [Q][66] candidates of a query
     float* sThr = reinterpret_cast<float*>(regB + kSelRegionB);                       // [Q]
@@ -705,18 +751,18 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
             return (unsigned short)(((u >> 31) ? u : u + 0xffffu) >> 16);
         };
 #pragma unroll 1
-        for (int c = part * (kSelGroups / kSelS); c < (part + 1) * (kSelGroups / kSelS); ++c) {
-            const int fb = (c * nfine) / kSelGroups, fe = ((c + 1) * nfine) / kSelGroups;  // at most 4 fine groups
-            float cmax = -CUDART_INF_F;
+        for (int c = part * kSelGpp; c < (part + 1) * kSelGpp; ++c) {
+            const int fb = (c * nfine) / kSelGroups, fe = ((c + 1) * nfine) / kSelGroups;  // at most 2 fine groups
+            float cmax = -CUDART_INF_F;  // maxima are taken before the query's norm is subtracted (knn_t3)
             if (fsh == 3) {  // one octet per fine group (N <= 1024): no inner loop
 #pragma unroll 2
                 for (int f = fb; f < fe; ++f) {
                     const float4* tp = sTile + (f << 3);
                     float p[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) p[u] = knn_pd3(q, xxi, tp[u]);
+                    for (int u = 0; u < 8; ++u) p[u] = knn_t3(q, tp[u]);
                     const float m = max3(max3(max3(p[0], p[1], p[2]), p[3], p[4]), max3(p[5], p[6], p[7]), p[0]);
-                    fm[f] = up16(m);
+                    fm[f] = up16(__fsub_rn(m, xxi));
                     cmax = fmaxf(cmax, m);
                 }
             } else {
@@ -727,45 +773,61 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
                     for (int o = 0; o < octs; ++o, tp += 8) {
                         float p[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) p[u] = knn_pd3(q, xxi, tp[u]);
+                        for (int u = 0; u < 8; ++u) p[u] = knn_t3(q, tp[u]);
                         m0 = max3(max3(m0, p[0], p[1]), p[2], p[3]);
                         m1 = max3(max3(m1, p[4], p[5]), p[6], p[7]);
                     }
                     const float m = max3(m0, m0, m1);
-                    fm[f] = up16(m);
+                    fm[f] = up16(__fsub_rn(m, xxi));
                     cmax = fmaxf(cmax, m);
                 }
             }
-            sScr[c * kSelQ + ql] = cmax;
+            sScr[c * kSelQ + ql] = __fsub_rn(cmax, xxi);
         }
     }
-    __syncthreads();
 
-    // ---- threshold: k-th largest of the 32 coarse group maxima (bitonic network in registers) ----
-    if (part == 0) {
-        float v[kSelGroups];
+    // ---- threshold: k-th largest of the 64 coarse group maxima. Every thread sorts the 16 maxima it has just produced (no
+    // barrier needed: its own values); the first thread of a query then merges the four sorted runs, keeping the 32 largest ----
+    {
+        float v[kSelGpp];
 #pragma unroll
-        for (int c = 0; c < kSelGroups; ++c) v[c] = sScr[c * kSelQ + ql];
+        for (int r = 0; r < kSelGpp; ++r) v[r] = sScr[(part * kSelGpp + r) * kSelQ + ql];
+        regs_sort_desc<kSelGpp>(v);
+        if (part != 0) {
 #pragma unroll
-        for (int s = 2; s <= kSelGroups; s <<= 1) {
-#pragma unroll
-            for (int d = s >> 1; d > 0; d >>= 1) {
-#pragma unroll
-                for (int e = 0; e < kSelGroups; ++e) {
-                    const int p = e ^ d;
-                    if (p > e) {
-                        const bool desc = (s == kSelGroups) || ((e & s) == 0);
-                        const float hi = fmaxf(v[e], v[p]), lo = fminf(v[e], v[p]);
-                        v[e] = desc ? hi : lo;
-                        v[p] = desc ? lo : hi;
-                    }
-                }
-            }
+            for (int r = 0; r < kSelGpp; ++r) sScr[(part * kSelGpp + r) * kSelQ + ql] = v[r];
         }
-        // v[k-1] without dynamic register indexing: through shared memory
+        __syncthreads();
+        if (part == 0) {
+            float t[32];
+            // run 0 (registers) and run 1: the half-cleaner leaves the 16 largest of the 32 in t[0..15], all >= t[16..31], both bitonic
 #pragma unroll
-        for (int c = 0; c < kSelGroups; ++c) sScr[c * kSelQ + ql] = v[c];
-        sThr[ql] = sScr[(k - 1) * kSelQ + ql];
+            for (int r = 0; r < kSelGpp; ++r) {
+                const float o = sScr[(kSelGpp + (kSelGpp - 1 - r)) * kSelQ + ql];
+                t[r] = fmaxf(v[r], o);
+                t[kSelGpp + r] = fminf(v[r], o);
+            }
+            {
+                float hi[kSelGpp], lo[kSelGpp];
+#pragma unroll
+                for (int r = 0; r < kSelGpp; ++r) hi[r] = t[r], lo[r] = t[kSelGpp + r];
+                regs_merge_desc<kSelGpp>(hi);
+                regs_merge_desc<kSelGpp>(lo);
+#pragma unroll
+                for (int r = 0; r < kSelGpp; ++r) t[r] = hi[r], t[kSelGpp + r] = lo[r];
+            }
+            // runs 2 and 3: the 32 largest of (t, run) are max(t[i], run[31 - i]) with the run padded by -inf: a bitonic sequence again
+#pragma unroll
+            for (int run = 2; run < kSelS; ++run) {
+#pragma unroll
+                for (int r = 0; r < kSelGpp; ++r) t[31 - r] = fmaxf(t[31 - r], sScr[(run * kSelGpp + r) * kSelQ + ql]);
+                regs_merge_desc<32>(t);
+            }
+            // t[k-1] without dynamic register indexing: through shared memory (this thread's own slots)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) sScr[c * kSelQ + ql] = t[c];
+            sThr[ql] = sScr[(k - 1) * kSelQ + ql];
+        }
     }
     __syncthreads();
     const float thr = sThr[ql];
@@ -889,8 +951,8 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
 #pragma unroll
         for (int z = 0; z < 2; ++z) {
             if (iq[z] < 0) continue;  // warp-uniform
-            if (c[z] < 0) {
-                // more than 64 candidates tie with the threshold: streaming sort-and-merge over the whole cloud
+            if (c[z] < 0 || c[z] < k) {
+                // more than 64 candidates tie with the threshold (or, with NaN scores, fewer than k reach it): streaming sort-and-merge over the whole cloud
                 u64 kk = 0ull, tau = 0ull;
                 for (int j0 = 0; j0 < N; j0 += 32) {
                     const int j = j0 + lane;

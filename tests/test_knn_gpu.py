@@ -108,6 +108,22 @@ def test_knn_vs_torch_reference_formula_on_gpu():
         assert float((got == ref).float().mean()) > 0.995
 
 
+@pytest.mark.parametrize("C,N,k", [(3, 1024, 20), (3, 300, 5), (3, 2048, 32), (16, 300, 20)])
+def test_knn_non_finite_inputs_terminate_with_indices_in_range(C, N, k):
+    """NaN / Inf coordinates (include/fpsg_b200.h: the ranking of NaN scores is unspecified): no hang, every index in [0, N),
+    and the clouds without a non-finite value are unaffected."""
+    import fpsg_b200
+    from oracle import cpu_oracle as O
+    x = make_cloud_cn(4, C, N, seed=41)
+    x[0, 1, 7] = float("nan")
+    x[1, 0, 9] = float("inf")
+    x[2, :, 11] = float("-inf")
+    idx = fpsg_b200.knn(x.cuda(), k)
+    torch.cuda.synchronize()
+    assert int(idx.min()) >= 0 and int(idx.max()) < N
+    assert np.array_equal(idx[3].cpu().numpy(), O.knn_f32(x[3:4].numpy(), k)[0])
+
+
 def test_knn_error_behaviour():
     import fpsg_b200
     x = torch.zeros(2, 3, 16, device="cuda")
