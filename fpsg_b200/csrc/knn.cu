@@ -654,6 +654,41 @@ __device__ __forceinline__ void regs_sort_desc(float (&v)[NV]) {
     }
 }
 
+__device__ __forceinline__ void u64_cmpx(u64& a, u64& b) {  // a = larger, b = smaller
+    const bool sw = a < b;
+    const u64 hi = sw ? b : a, lo = sw ? a : b;
+    a = hi;
+    b = lo;
+}
+template <int NV>
+__device__ __forceinline__ void regs_merge_desc(u64 (&v)[NV]) {  // bitonic sequence -> descending
+#pragma unroll
+    for (int d = NV >> 1; d > 0; d >>= 1) {
+#pragma unroll
+        for (int e = 0; e < NV; ++e)
+            if ((e & d) == 0) u64_cmpx(v[e], v[e | d]);
+    }
+}
+template <int NV>
+__device__ __forceinline__ void regs_sort_desc(u64 (&v)[NV]) {
+#pragma unroll
+    for (int s = 2; s <= NV; s <<= 1) {
+#pragma unroll
+        for (int d = s >> 1; d > 0; d >>= 1) {
+#pragma unroll
+            for (int e = 0; e < NV; ++e) {
+                const int p = e ^ d;
+                if (p > e) {
+                    if ((s == NV) || ((e & s) == 0))
+                        u64_cmpx(v[e], v[p]);
+                    else
+                        u64_cmpx(v[p], v[e]);
+                }
+            }
+        }
+    }
+}
+
 // sorts two independent key sets at once (the two shuffle chains overlap: the stage is latency-bound otherwise)
 __device__ __forceinline__ void warp_sort_desc2(u64& a, u64& b, int lane) {
 #pragma unroll
@@ -687,6 +722,7 @@ constexpr size_t kSelFmBytes = (size_t)kSelQ * kSelFmStride * sizeof(unsigned sh
 static_assert(kSelFmBytes % 16 == 0 && kSelFmBytes + (size_t)kSelGroups * kSelQ * sizeof(float) <= kSelRegionA + kSelRegionB,
               "the exact coarse maxima ([64][Q] floats) fit behind the fine maxima: the tail of region A and all of region B");
 static_assert(kSelRegionB >= (size_t)(kSelFine / kSelS) * kSelThreads, "region B holds the per-thread group lists");
+static_assert((size_t)(kSelThreads / 32) * 256 * sizeof(unsigned short) <= kSelRegionB, "the warps' sorted indices of the final phase fit region B");
 static KnnSelPlan knn_select_plan(int N) {
     KnnSelPlan p;
     p.fsh = 3;
@@ -694,7 +730,7 @@ static KnnSelPlan knn_select_plan(int N) {
     p.nfine = (N + (1 << p.fsh) - 1) >> p.fsh;
     p.npad = p.nfine << p.fsh;
     p.smem = (size_t)(p.npad + (1 << p.fsh)) * sizeof(float4) + kSelRegionA + kSelRegionB + (size_t)kSelQ * sizeof(float) +
-             (size_t)kSelThreads * sizeof(signed char) + (size_t)kSelQ * sizeof(signed char);  // ~50 KB at N = 1024: four CTAs per SM
+             2 * (size_t)kSelThreads * sizeof(signed char);  // ~50 KB at N = 1024: four CTAs per SM
     return p;
 }
 
@@ -710,10 +746,9 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     unsigned short* sBuf = reinterpret_cast<unsigned short*>(regA);                   // ... then [48][T] candidate columns
     float* sScr = reinterpret_cast<float*>(regA + kSelFmBytes);                       // [64][Q] exact coarse maxima (then sorted): tail of A + B ...
     unsigned char* sGl = regB;                                                        // ... then [32][T] fine groups to re-score ...
-    unsigned short* sList = reinterpret_cast<unsigned short*>(regB);                  // ... then [Q][66] candidates of a query
     float* sThr = reinterpret_cast<float*>(regB + kSelRegionB);                       // [Q]
     signed char* sCntP = reinterpret_cast<signed char*>(sThr + kSelQ);                // [T] candidates found by a thread, -1 = overflow
-    signed char* sCnt = sCntP + kSelThreads;                                          // [Q] candidates of a query, -1 = overflow
+    unsigned char* sNgl = reinterpret_cast<unsigned char*>(sCntP + kSelThreads);      // [T] fine groups a thread has listed
 
     // the warp index through a shuffle: the compiler then knows it is warp-uniform (and with it every loop bound derived from it)
     const int tid = threadIdx.x, lane = tid & 31, w = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -842,13 +877,16 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
             ngl += __uint_as_float((unsigned)fm[f] << 16) >= thr ? 1 : 0;
         }
     }
+    sNgl[tid] = (unsigned char)ngl;
     __syncthreads();  // every read of the fine maxima is done: their region becomes the candidate columns
 
     // ---- re-score the listed groups: indices of the candidates with pd >= thr go to this thread's column ----
+    // The four lists of a query are taken as one (positions 0 .. total-1) and dealt round-robin to its four threads: a warp walks
+    // max over its lanes of ceil(total / 4) groups instead of the longest private list (7.5 instead of 10.5 at c3).
     {
-        int wmax = ngl;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        const int qb = wq * kSelS * 32 + lane;
+        const int b1 = sNgl[qb], b2 = b1 + sNgl[qb + 32], b3 = b2 + sNgl[qb + 64], total = b3 + sNgl[qb + 96];
+        const int wmax = __reduce_max_sync(0xffffffffu, (total - part + kSelS - 1) >> 2);
         const unsigned col = static_cast<unsigned>(__cvta_generic_to_shared(sBuf + tid));
         const unsigned stepb = 2u * kSelThreads;
         const unsigned limit = col + (kSelColCap - 8) * stepb;
@@ -856,7 +894,13 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
         bool ovf = false;
 #pragma unroll 1
         for (int g = 0; g < wmax; ++g) {
-            const int f = g < ngl ? (int)sGl[g * kSelThreads + tid] : nfine;  // idle lanes score the all-padding group
+            const int pos = g * kSelS + part;
+            int f = nfine;  // idle lanes score the all-padding group
+            if (pos < total) {
+                const int pp = (pos >= b1 ? 1 : 0) + (pos >= b2 ? 1 : 0) + (pos >= b3 ? 1 : 0);  // whose list, and where in it
+                const int li = pos - (pos >= b3 ? b3 : pos >= b2 ? b2 : pos >= b1 ? b1 : 0);
+                f = (int)sGl[li * kSelThreads + qb + pp * 32];
+            }
             const int j0 = f << fsh;
 #pragma unroll 1
             for (int o = 0; o < octs; ++o) {
@@ -888,75 +932,107 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     }
     __syncthreads();
 
-    // ---- the four shares of a query, concatenated into its row of sList ----
+    // ---- final: the candidates of a query (its four columns taken as one list) sorted, the first k indices written ----
+    // Common case, k <= candidates <= 32: warp w takes the CTA's queries 8w .. 8w+7, four lanes per query. The 32 keys of a query are
+    // a bitonic network spread over the registers of its four lanes -- 8 keys each, sorted locally, then three exchange steps with
+    // the partner lane (its keys read reversed or straight, the larger or the smaller half kept) and local 8-key merges in between:
+    // one instruction serves 32 (query, quarter) pairs, where a warp-wide network serves one query (8 M -> 2 M warp-instructions at
+    // c3), and nothing but shuffles passes between lanes -- no barrier, no shared-memory round trip.
     {
-        int before = 0, total = 0;
-        bool ovf = false;
+        const unsigned short* sCol = sBuf;
+        const int ql2 = w * 8 + (lane >> 2), pr = lane & 3;
+        const int i2 = blockIdx.x * kSelQ + ql2;
+        const int colbase = (ql2 >> 5) * (kSelS * 32) + (ql2 & 31);  // column of the query's first share; the others follow 32 apart
+        const int c0 = sCntP[colbase], c1 = sCntP[colbase + 32], c2 = sCntP[colbase + 64], c3 = sCntP[colbase + 96];
+        const bool ovf = (c0 | c1 | c2 | c3) < 0;
+        const int b1 = c0, b2 = b1 + c1, b3 = b2 + c2, total = b3 + c3;
+        const bool fast = i2 < N && !ovf && total >= k && total <= 32;
+        const float4 q2 = sTile[min(i2, N - 1)];
+        // entry e of a query's list: which column, and where in it
+        auto cand = [&](int e, int cb, int e1, int e2, int e3) {
+            const int pp = (e >= e1 ? 1 : 0) + (e >= e2 ? 1 : 0) + (e >= e3 ? 1 : 0);
+            const int li = e - (e >= e3 ? e3 : e >= e2 ? e2 : e >= e1 ? e1 : 0);
+            return (int)sCol[li * kSelThreads + cb + pp * 32];
+        };
+        u64 key[8];
 #pragma unroll
-        for (int pp = 0; pp < kSelS; ++pp) {
-            const int c = sCntP[(wq * kSelS + pp) * 32 + lane];
-            ovf |= c < 0;
-            if (pp < part) before += c;
-            total += c;
+        for (int r = 0; r < 8; ++r) {
+            key[r] = 0ull;
+            if (fast && pr * 8 + r < total) {
+                const int j = cand(pr * 8 + r, colbase, b1, b2, b3);
+                key[r] = knn_key_of(knn_pd3(q2, -q2.w, sTile[j]), j);
+            }
         }
-        ovf |= total > kSelCap;
-        if (!ovf) {
-            const int mine = sCntP[tid];
-            for (int e = 0; e < mine; ++e) sList[ql * kSelListStride + before + e] = sBuf[e * kSelThreads + tid];
+        regs_sort_desc<8>(key);
+        auto exchange = [&](const int mask, const bool reversed, const bool keep_max) {
+            u64 o[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) o[r] = __shfl_xor_sync(0xffffffffu, key[reversed ? 7 - r : r], mask);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) key[r] = ((key[r] > o[r]) == keep_max) ? key[r] : o[r];
+        };
+        exchange(1, true, (pr & 1) == 0);  // 2 x 8 -> 16 (two bitonic halves), sorted by the local merge
+        regs_merge_desc<8>(key);
+        exchange(3, true, pr < 2);         // 2 x 16 -> the upper 16 in lanes 0, 1 of the query, the lower 16 in lanes 2, 3
+        exchange(1, false, (pr & 1) == 0);
+        regs_merge_desc<8>(key);
+        // The sorted indices go through (warp-private) shared memory so that the warp's 8 x k indices leave as contiguous 256-byte
+        // stores (written from the registers, every store instruction would touch 24 different 32-byte sectors for 8 bytes each).
+        unsigned short* so = reinterpret_cast<unsigned short*>(regB) + w * 256;  // [8 queries][32 ranks]; the group lists are dead
+        {
+            unsigned pk[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                pk[r] = ((0xffffffffu - (unsigned)key[2 * r]) & 0xffffu) | ((0xffffffffu - (unsigned)key[2 * r + 1]) << 16);
+            reinterpret_cast<uint4*>(so)[lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        if (part == 0) sCnt[ql] = ovf ? (signed char)-1 : (signed char)total;
-    }
-    __syncthreads();
+        const unsigned fmask = __ballot_sync(0xffffffffu, fast);
+        __syncwarp();
+        {
+            const unsigned inv = (65536u + (unsigned)k - 1u) / (unsigned)k;  // e / k for e < 256, k <= 32: exact
+            int64_t* __restrict__ out = idx + ((size_t)b * N + (size_t)blockIdx.x * kSelQ + w * 8) * k;
+            for (int e = lane; e < 8 * k; e += 32) {
+                const int qq = (int)(((unsigned)e * inv) >> 16), r = e - qq * k;
+                if ((fmask >> (qq * 4)) & 1u) out[e] = (int64_t)so[qq * 32 + r];
+            }
+        }
 
-    // ---- final: a warp sorts the candidates of its queries, two queries at a time, and writes the first k ----
+        // The rest -- more than 32 candidates, an overflow of a column, or (NaN scores) fewer than k candidates: the whole warp
+        // sorts one such query at a time.
+        unsigned todo = __ballot_sync(0xffffffffu, pr == 0 && i2 < N && !fast);
+        while (todo != 0u) {  // warp-uniform
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int tot = __shfl_sync(0xffffffffu, ovf ? -1 : total, src);
+            const int cb = __shfl_sync(0xffffffffu, colbase, src);
+            const int e1 = __shfl_sync(0xffffffffu, b1, src), e2 = __shfl_sync(0xffffffffu, b2, src), e3 = __shfl_sync(0xffffffffu, b3, src);
+            const int iq = blockIdx.x * kSelQ + w * 8 + (src >> 2);
+            const float4 qp = sTile[iq];
+            u64 kk = 0ull;
+            if (tot >= k && tot <= kSelCap) {
 #pragma unroll 1
-    for (int n = 0; n < 32 / kSelS; n += 2) {
-        int tq[2], iq[2], c[2];
-        float4 qp[2];
-        u64 key[2];
-#pragma unroll
-        for (int z = 0; z < 2; ++z) {
-            tq[z] = wq * 32 + part + (n + z) * kSelS;
-            iq[z] = blockIdx.x * kSelQ + tq[z];
-            if (iq[z] >= N) iq[z] = -1;  // warp-uniform
-            // one value per warp (the same shared-memory word for all lanes); REDUX tells the compiler so: the loop bounds below are
-            // warp-uniform and the shuffles of the sorting networks need no convergence wrappers (174 of 349 had one)
-            c[z] = __reduce_max_sync(0xffffffffu, iq[z] >= 0 ? (int)sCnt[tq[z]] : 0);
-            qp[z] = sTile[max(iq[z], 0)];
-            key[z] = 0ull;
-        }
-#pragma unroll 1
-        for (int h = 0; h * 32 < max(c[0], c[1]); ++h) {
-            const int e = h * 32 + lane;
-            u64 kb[2];
-#pragma unroll
-            for (int z = 0; z < 2; ++z) {
-                kb[z] = 0ull;
-                if (e < c[z]) {
-                    const int j = sList[tq[z] * kSelListStride + e];
-                    kb[z] = knn_key_of(knn_pd3(qp[z], -qp[z].w, sTile[j]), j);
+                for (int h = 0; h * 32 < tot; ++h) {
+                    const int e = h * 32 + lane;
+                    u64 kb = 0ull;
+                    if (e < tot) {
+                        const int j = cand(e, cb, e1, e2, e3);
+                        kb = knn_key_of(knn_pd3(qp, -qp.w, sTile[j]), j);
+                    }
+                    kb = warp_sort_desc(kb, lane);
+                    if (h == 0) {
+                        kk = kb;
+                    } else {
+                        const u64 rev = __shfl_sync(0xffffffffu, kb, 31 - lane);
+                        kk = warp_merge_desc(kk > rev ? kk : rev, lane);
+                    }
                 }
-            }
-            warp_sort_desc2(kb[0], kb[1], lane);
-            if (h == 0) {
-                key[0] = kb[0];
-                key[1] = kb[1];
             } else {
-                const u64 r0 = __shfl_sync(0xffffffffu, kb[0], 31 - lane), r1 = __shfl_sync(0xffffffffu, kb[1], 31 - lane);
-                key[0] = key[0] > r0 ? key[0] : r0;
-                key[1] = key[1] > r1 ? key[1] : r1;
-                warp_merge_desc2(key[0], key[1], lane);
-            }
-        }
-#pragma unroll
-        for (int z = 0; z < 2; ++z) {
-            if (iq[z] < 0) continue;  // warp-uniform
-            if (c[z] < 0 || c[z] < k) {
-                // more than 64 candidates tie with the threshold (or, with NaN scores, fewer than k reach it): streaming sort-and-merge over the whole cloud
-                u64 kk = 0ull, tau = 0ull;
+                // more than 64 candidates tie with the threshold, a column overflowed, or fewer than k candidates reach a NaN-ridden
+                // threshold: streaming sort-and-merge over the whole cloud
+                u64 tau = 0ull;
                 for (int j0 = 0; j0 < N; j0 += 32) {
                     const int j = j0 + lane;
-                    u64 kb = j < N ? knn_key_of(knn_pd3(qp[z], -qp[z].w, sTile[j]), j) : 0ull;
+                    u64 kb = j < N ? knn_key_of(knn_pd3(qp, -qp.w, sTile[j]), j) : 0ull;
                     if (!(kb > tau)) kb = 0ull;
                     if (__any_sync(0xffffffffu, kb != 0ull)) {
                         kb = warp_sort_desc(kb, lane);
@@ -965,9 +1041,8 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
                         tau = __shfl_sync(0xffffffffu, kk, k - 1);
                     }
                 }
-                key[z] = kk;
             }
-            if (lane < k) idx[((size_t)b * N + iq[z]) * k + lane] = (int64_t)(0xffffffffu - (unsigned)key[z]);
+            if (lane < k) idx[((size_t)b * N + iq) * k + lane] = (int64_t)(0xffffffffu - (unsigned)kk);
         }
     }
 }
