@@ -785,6 +785,22 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
             const unsigned u = __float_as_uint(v);
             return (unsigned short)(((u >> 31) ? u : u + 0xffffu) >> 16);
         };
+        if (fsh == 3 && nfine == 2 * kSelGroups) {  // 896 < N <= 1024 (c3): every coarse group is exactly two octets, no loop control at all
+#pragma unroll 1
+            for (int c = part * kSelGpp; c < (part + 1) * kSelGpp; ++c) {
+                const float4* tp = sTile + (c << 4);
+                float m2[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float p[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) p[u] = knn_t3(q, tp[8 * h + u]);
+                    m2[h] = max3(max3(max3(p[0], p[1], p[2]), p[3], p[4]), max3(p[5], p[6], p[7]), p[0]);
+                }
+                *reinterpret_cast<unsigned*>(fm + 2 * c) = (unsigned)up16(__fsub_rn(m2[0], xxi)) | ((unsigned)up16(__fsub_rn(m2[1], xxi)) << 16);
+                sScr[c * kSelQ + ql] = __fsub_rn(fmaxf(m2[0], m2[1]), xxi);
+            }
+        } else
 #pragma unroll 1
         for (int c = part * kSelGpp; c < (part + 1) * kSelGpp; ++c) {
             const int fb = (c * nfine) / kSelGroups, fe = ((c + 1) * nfine) / kSelGroups;  // at most 2 fine groups
@@ -871,11 +887,29 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     int ngl = 0;
     {
         const unsigned short* fm = sFm + ql * kSelFmStride;
-        unsigned char* gl = sGl + tid;
-        for (int f = f0; f < f1; ++f) {
-            gl[ngl * kSelThreads] = (unsigned char)f;
-            ngl += __uint_as_float((unsigned)fm[f] << 16) >= thr ? 1 : 0;
+        const unsigned gl0 = static_cast<unsigned>(__cvta_generic_to_shared(sGl + tid));
+        unsigned gp = gl0;  // an unconditional byte store and a predicated cursor bump per group (inline PTX, as in the re-scoring below)
+        auto push = [&](int f, unsigned bits) {
+            asm volatile(
+                "{\n\t.reg .pred pp;\n\t"
+                "st.shared.u8 [%0], %1;\n\t"
+                "setp.ge.f32 pp, %2, %3;\n\t"
+                "@pp add.u32 %0, %0, %4;\n\t}"
+                : "+r"(gp)
+                : "r"(f), "f"(__uint_as_float(bits)), "f"(thr), "n"(kSelThreads)
+                : "memory");
+        };
+        if (((f0 | f1) & 1) == 0) {  // two maxima per load (rows are 4-byte aligned: kSelFmStride is even)
+#pragma unroll 4
+            for (int f = f0; f < f1; f += 2) {
+                const unsigned two = *reinterpret_cast<const unsigned*>(fm + f);
+                push(f, two << 16);
+                push(f + 1, two & 0xffff0000u);
+            }
+        } else {
+            for (int f = f0; f < f1; ++f) push(f, (unsigned)fm[f] << 16);
         }
+        ngl = (int)((gp - gl0) / kSelThreads);
     }
     sNgl[tid] = (unsigned char)ngl;
     __syncthreads();  // every read of the fine maxima is done: their region becomes the candidate columns
@@ -887,6 +921,9 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
         const int qb = wq * kSelS * 32 + lane;
         const int b1 = sNgl[qb], b2 = b1 + sNgl[qb + 32], b3 = b2 + sNgl[qb + 64], total = b3 + sNgl[qb + 96];
         const int wmax = __reduce_max_sync(0xffffffffu, (total - part + kSelS - 1) >> 2);
+        int rot[8];  // (u + lane) & 7, pinned: the compiler otherwise recomputes all eight in every iteration of the group loop
+#pragma unroll
+        for (int u = 0; u < 8; ++u) asm volatile("and.b32 %0, %1, 7;" : "=r"(rot[u]) : "r"(u + lane));
         const unsigned col = static_cast<unsigned>(__cvta_generic_to_shared(sBuf + tid));
         const unsigned stepb = 2u * kSelThreads;
         const unsigned limit = col + (kSelColCap - 8) * stepb;
@@ -909,10 +946,10 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
                 const float4* tp = sTile + j0 + 8 * o;
                 float pd[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) pd[u] = knn_pd3(q, xxi, tp[(u + lane) & 7]);
+                for (int u = 0; u < 8; ++u) pd[u] = knn_pd3(q, xxi, tp[rot[u]]);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const unsigned short jv = (unsigned short)(j0 + 8 * o + ((u + lane) & 7));
+                    const unsigned short jv = (unsigned short)(j0 + 8 * o + rot[u]);
                     asm volatile(
                         "{\n\t.reg .pred pp;\n\t"
                         "st.shared.u16 [%0], %1;\n\t"
