@@ -50,7 +50,7 @@ N_LANES = 4     # streams (each with its own workspace and outputs) the independ
 # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch, from the ncu --set full capture named below (the
 # kernel streams its 1.573 MB of input once; a number taken under the profiler is cited, not re-measured in the timed run)
 SWEEP_DRAM_TRAFFIC_BYTES = 1.599e6
-SWEEP_DRAM_TRAFFIC_SOURCE = "profiles/r01g_chamfer_kernels_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, chamfer_sweep_kernel)"
+SWEEP_DRAM_TRAFFIC_SOURCE = "profiles/r02e_step_kernels_raw.csv / r02e_step_kernels_digest.txt (dram__bytes_read.sum + dram__bytes_write.sum = 1.5987 MB + 256 B, chamfer_sweep_kernel, final build)"
 
 
 def make_inputs(batch, n, m, seed, device=None, pin=False):
