@@ -372,19 +372,34 @@ def chamfer_loss_multi_and_grad(pairs, weights=None, w1: float = 1.0, w2: float 
     return out[0], out[1:1 + nseg], out[1 + nseg:], grads
 
 
+# One call of the library takes at most 65535 pairs (a grid dimension). Kaolin accepts any batch size, so larger batches go in
+# chunks: pairs are independent, and torch.cat keeps the pieces differentiable.
+_MAX_PAIRS_PER_CALL = 65535
+
+
+def _in_chunks(fn, p1: torch.Tensor, p2: torch.Tensor, *args):
+    B = p1.shape[0] if p1.dim() == 3 else 0
+    if B <= _MAX_PAIRS_PER_CALL or p2.dim() != 3 or p2.shape[0] != B:
+        return fn(p1, p2, *args)  # (shape errors are reported by the call itself)
+    outs = [fn(p1[s:s + _MAX_PAIRS_PER_CALL], p2[s:s + _MAX_PAIRS_PER_CALL], *args) for s in range(0, B, _MAX_PAIRS_PER_CALL)]
+    if isinstance(outs[0], tuple):
+        return tuple(torch.cat(o, dim=0) for o in zip(*outs))
+    return torch.cat(outs, dim=0)
+
+
 def chamfer_distance(p1: torch.Tensor, p2: torch.Tensor):
     """(dist1 (B,N), dist2 (B,M), idx1 (B,N) int64, idx2 (B,M) int64): squared-L2 nearest-neighbour distances in
     both directions and their arg-mins (lowest index on exact ties). Differentiable w.r.t. p1 and p2 through
     dist1/dist2; the index outputs are non-differentiable."""
-    return _ChamferDistance.apply(p1, p2)
+    return _in_chunks(_ChamferDistance.apply, p1, p2)
 
 
 def sided_distance(p1: torch.Tensor, p2: torch.Tensor):
     """Kaolin's ``sided_distance``: (dist (B,N), idx (B,N) int64) from every p1 point to its nearest p2 point."""
-    return _SidedDistance.apply(p1, p2)
+    return _in_chunks(_SidedDistance.apply, p1, p2)
 
 
 def chamfer_loss(p1: torch.Tensor, p2: torch.Tensor, w1: float = 1.0, w2: float = 1.0) -> torch.Tensor:
     """(B,) = w1 * mean_i dist1 + w2 * mean_j dist2 -- the tensor ``kaolin.metrics.pointcloud.chamfer_distance``
     returns and the reference sums (src/models/few_shot.py:110,117,167)."""
-    return _ChamferLoss.apply(p1, p2, float(w1), float(w2))
+    return _in_chunks(_ChamferLoss.apply, p1, p2, float(w1), float(w2))

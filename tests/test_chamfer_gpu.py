@@ -190,6 +190,30 @@ def test_fused_loss_matches_composed_and_weights():
     assert_close_rel(b.grad.cpu().numpy(), gb.cpu().numpy(), 1e-5, "grad_p2", scale_frac=1.0)
 
 
+def test_batches_beyond_one_call_are_chunked(monkeypatch):
+    """The library takes at most 65535 pairs per call (Kaolin: any batch size); the wrappers chunk and stay differentiable
+    (checked with a small chunk size: outputs and gradients identical to the one-call result)."""
+    import sys
+    import fpsg_b200
+    C = sys.modules["fpsg_b200.chamfer"]
+    p1, p2 = make_pair(7, 120, 90, seed=9)
+    go = torch.randn(7, device="cuda")
+
+    def run():
+        a, b = p1.cuda().requires_grad_(True), p2.cuda().requires_grad_(True)
+        d1, d2, i1, i2 = fpsg_b200.chamfer_distance(a, b)
+        loss = fpsg_b200.chamfer_loss(a, b, 0.5, 2.0)
+        sd, si = fpsg_b200.sided_distance(a, b)
+        ((loss * go).sum() + d1.sum() + 3.0 * d2.sum() + sd.sum()).backward()
+        return [t.detach().clone() for t in (d1, d2, i1, i2, loss, sd, si, a.grad, b.grad)]
+
+    whole = run()
+    monkeypatch.setattr(C, "_MAX_PAIRS_PER_CALL", 3)
+    parts = run()
+    for w_, p_ in zip(whole, parts):
+        assert w_.shape == p_.shape and torch.equal(w_, p_)
+
+
 def test_sided_distance_surface():
     import fpsg_b200
     O = _oracle()
