@@ -658,6 +658,26 @@ def main():
     e2e_s = sorted(e2e_reps)[1]
     pipe.close()
 
+    # ---- the floor under e2e: the same host->device copies alone (all ranks at once, nothing else running). On an 8-GPU box two
+    # GPUs share a PCIe switch uplink, so the copies of a step can take longer than its kernels; the line reports both ----
+    h2d_dst = [torch.empty_like(host[0][0], device=dev), torch.empty_like(host[0][1], device=dev)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_iters = 300
+
+    def h2d_only(n):
+        with torch.cuda.stream(copy_stream):
+            for i_ in range(n):
+                h1_, h2_ = host[i_ % len(host)]
+                h2d_dst[0].copy_(h1_, non_blocking=True)
+                h2d_dst[1].copy_(h2_, non_blocking=True)
+        copy_stream.synchronize()
+    h2d_only(50)
+    barrier()
+    t0 = time.perf_counter()
+    h2d_only(h2d_iters)
+    barrier()
+    h2d_s = time.perf_counter() - t0
+
     # ---- end to end through the reference-facing Python call with autograd: kaolin shim chamfer_distance(p1, p2).sum()
     # .backward(), one H2D copy per step from pinned memory, loss read back, stream synchronised every step ----
     fpsg_b200.shims.install(force=True)
@@ -690,9 +710,9 @@ def main():
 
     # ---- reduce over ranks (max time) ----
     if world > 1:
-        t = torch.tensor([ms, e2e_s, ag_s, ms_nocoll, ms_lag0, ms_serial], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, ag_s, ms_nocoll, ms_lag0, ms_serial, h2d_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, ag_s, ms_nocoll, ms_lag0, ms_serial = (float(v) for v in t)
+        ms, e2e_s, ag_s, ms_nocoll, ms_lag0, ms_serial, h2d_s = (float(v) for v in t)
 
     if rank == 0:
         pairs = world * B
@@ -718,6 +738,10 @@ def main():
                        "parity": "Chamfer oracle is parity-unpinned (Kaolin 0.9.0 absent): bit-exact vs the restated algorithm; kNN and input pipeline pinned"},
             "e2e": {"value": pairs * e2e_steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": (2 + B + _lib.PEER_RING) * 4,
                     "steps": e2e_steps, "passes_pairs_per_s": [pairs * e2e_steps / t_ for t_ in e2e_reps], "reported": "median of three passes",
+                    "h2d_copies_alone": {"gb_per_s_per_gpu": B * (N + M) * 12 * h2d_iters / h2d_s / 1e9, "us_per_step": h2d_s / h2d_iters * 1e6,
+                                         "pairs_per_s_ceiling": pairs * h2d_iters / h2d_s,
+                                         "what": "the same pinned-host -> device copies with nothing else running, all ranks at once (max over ranks): "
+                                                 "when this exceeds ms_per_step the host link, not the kernels, bounds e2e"},
                     "api": "fpsg_chamfer_pipeline_submit / _result (include/fpsg_b200.h; fpsg_b200.ChamferPipeline): every step copies its own inputs "
                            "from pinned HOST memory, runs sweep + finish and reads its per-pair losses and their sum back to the host (with the ring of all-reduced sums); depth " + str(DEPTH) + ", so the "
                            "H2D copies of step i+1 overlap the kernels of step i; the gradient stays on the device as in the reference"},
