@@ -64,8 +64,15 @@ edge_feature_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__
 
 // inverted index of idx for one cloud: for every point n the list of slots e = n'*k + j with idx[e] == n.
 // start (N+1 ints) and list (N*k ints) live in the workspace. One CTA per cloud; counts in shared memory.
+// For the plane-staged backward the buckets are also cut into SUB-BUCKETS of at most kPlaneSub entries (kNN graphs of
+// high-dimensional features have hubs: a fifth of the points of a 64-channel cloud have more than 32 in-edges, some several
+// hundred): vfirst[n] = number of sub-buckets of the points before n (N+1 entries), vbeg[v] = first list position of
+// sub-bucket v (sub-buckets are consecutive pieces of the list; vbeg[V] = N*k). Both 16-bit (that path needs N*k <= 65535).
+constexpr int kPlaneSub = 16;
+
 __global__ void __launch_bounds__(1024)
-edge_invert_kernel(const int64_t* __restrict__ idx, int N, int k, int* __restrict__ start_all, int* __restrict__ list_all) {
+edge_invert_kernel(const int64_t* __restrict__ idx, int N, int k, int* __restrict__ start_all, int* __restrict__ list_all,
+                   unsigned short* __restrict__ vfirst_all, unsigned short* __restrict__ vbeg_all, int vstride) {
     extern __shared__ int sCnt[];  // N + 1 counters, then reused as cursors
     __shared__ int sWarp[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -79,39 +86,59 @@ edge_invert_kernel(const int64_t* __restrict__ idx, int N, int k, int* __restric
 #pragma unroll 8
     for (long long e = tid; e < nk; e += 1024) atomicAdd(&sCnt[(int)ib[e]], 1);
     __syncthreads();
-    // exclusive scan over N counters, 1024 threads, chunked
-    int carry = 0;
-    for (int base = 0; base < N; base += 1024) {
-        const int n = base + tid;
-        const int c = n < N ? sCnt[n] : 0;
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) sWarp[w] = incl;
-        __syncthreads();
-        if (w == 0) {
-            int v = sWarp[lane];
+    // exclusive scan over N values, 1024 threads, chunked; value(n) is given by f, the result handed to out(n, exclusive prefix)
+    auto scan = [&](auto f, auto out) {
+        int carry = 0;
+        for (int base = 0; base < N; base += 1024) {
+            const int n = base + tid;
+            const int c = n < N ? f(n) : 0;
+            int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, v, o);
-                if (lane >= o) v += u;
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            sWarp[lane] = v;  // inclusive over warps
+            if (lane == 31) sWarp[w] = incl;
+            __syncthreads();
+            if (w == 0) {
+                int v = sWarp[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += u;
+                }
+                sWarp[lane] = v;  // inclusive over warps
+            }
+            __syncthreads();
+            const int excl = carry + (w > 0 ? sWarp[w - 1] : 0) + incl - c;
+            const int total = sWarp[31];
+            __syncthreads();
+            if (n < N) out(n, excl, c);
+            carry += total;
         }
-        __syncthreads();
-        const int excl = carry + (w > 0 ? sWarp[w - 1] : 0) + incl - c;
-        const int total = sWarp[31];
-        __syncthreads();
-        if (n < N) {
-            start[n] = excl;
-            sCnt[n] = excl;  // cursor
+        return carry;
+    };
+    if (vfirst_all != nullptr) {  // sub-bucket tables (before the counters turn into cursors)
+        unsigned short* __restrict__ vfirst = vfirst_all + (size_t)b * (N + 1);
+        unsigned short* __restrict__ vbeg = vbeg_all + (size_t)b * vstride;
+        const int V = scan([&](int n) { return (sCnt[n] + kPlaneSub - 1) / kPlaneSub; },
+                           [&](int n, int excl, int) { vfirst[n] = (unsigned short)excl; });
+        if (tid == 0) {
+            vfirst[N] = (unsigned short)V;
+            vbeg[V] = (unsigned short)nk;
         }
-        carry += total;
+        __syncthreads();  // vfirst is read back below by other threads' points? no: each thread reads its own n -- but keep the scan's sWarp settled
     }
-    if (tid == 0) start[N] = carry;
+    const int total = scan([&](int n) { return sCnt[n]; },
+                           [&](int n, int excl, int c) {
+                               start[n] = excl;
+                               if (vfirst_all != nullptr) {
+                                   unsigned short* __restrict__ vbeg = vbeg_all + (size_t)b * vstride + vfirst_all[(size_t)b * (N + 1) + n];
+                                   for (int j = 0; j * kPlaneSub < c; ++j) vbeg[j] = (unsigned short)(excl + j * kPlaneSub);
+                               }
+                               sCnt[n] = excl;  // cursor
+                           });
+    if (tid == 0) start[N] = total;
     __syncthreads();
 #pragma unroll 8
     for (long long e = tid; e < nk; e += 1024) list[atomicAdd(&sCnt[(int)ib[e]], 1)] = (int)e;
@@ -154,29 +181,31 @@ edge_feature_bwd_kernel(const float* __restrict__ g, const int* __restrict__ sta
 }
 
 // Plane-staged backward: CTA g owns the planes [g*P/G, (g+1)*P/G) of the flattened (cloud, channel) range.
+// Per plane: (A) the sub-buckets of the cloud's inverted index are dealt round-robin to the 1024 threads -- at most kPlaneSub
+// gathers each, whatever the in-degree of their point, so a hub costs its point's thread nothing extra -- and their sums go to
+// shared memory as doubles; (B) every point's thread adds its own k slots, the centre half and its sub-bucket sums in index
+// order (a fixed order: the result does not depend on the schedule).
 constexpr int kPlaneThreads = 1024;
 constexpr int kPlaneK4 = 5;  // k <= 20 on this path (DGCNN uses 20)
-constexpr int kHubCap = 32;  // bucket entries a point's own thread gathers; the rest of a longer bucket ("hub" point: kNN graphs
-                             // of high-dimensional features have a few points with hundreds of in-edges) is summed by a whole warp
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 
+static int edge_plane_vmax(int N, int k) { return (int)(((long long)N * k) / kPlaneSub) + N; }  // sub-buckets of a cloud, at most
+
 __global__ void __launch_bounds__(kPlaneThreads, 1)
-edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict__ start_all, const int* __restrict__ list_all, int B, int C,
-                              int N, int k, float* __restrict__ gx) {
+edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict__ list_all, const unsigned short* __restrict__ vfirst_all,
+                              const unsigned short* __restrict__ vbeg_all, int vmax, int B, int C, int N, int k, float* __restrict__ gx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nk = N * k;
-    float* sPlane = reinterpret_cast<float*>(smem_raw);                          // [2][nk] difference-half planes
-    int* sStart = reinterpret_cast<int*>(sPlane + 2 * (size_t)nk);                // [N + 1]
-    unsigned short* sList = reinterpret_cast<unsigned short*>(sStart + N + 1);    // [nk] slots, grouped by target point
-    __shared__ unsigned short sHub[kPlaneThreads];  // hub points of the current cloud
-    __shared__ double sHubAcc[kPlaneThreads];       // their partial sums between the two phases
-    __shared__ int sNHub;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    int myslot = -1;  // this thread's point is hub number myslot of the current cloud
+    float* sPlane = reinterpret_cast<float*>(smem_raw);                            // [2][nk] difference-half planes
+    double* sPart = reinterpret_cast<double*>(sPlane + 2 * (size_t)nk);             // [vmax] sub-bucket sums of the current plane
+    unsigned short* sList = reinterpret_cast<unsigned short*>(sPart + vmax);       // [nk] slots, grouped by target point
+    unsigned short* sVbeg = sList + nk;                                            // [vmax + 1]
+    unsigned short* sVfirst = sVbeg + vmax + 1;                                    // [N + 1]
+    const int tid = threadIdx.x;
     const long long planes = (long long)B * C;
     const int p0 = (int)(planes * blockIdx.x / gridDim.x), p1 = (int)(planes * (blockIdx.x + 1) / gridDim.x);
 
@@ -209,7 +238,7 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
     };
     double msum = 0.0;
 
-    int cur_b = -1;
+    int cur_b = -1, V = 0;
     if (p0 < p1) {
         prefetch(p0, 0);
         load_centre(p0);
@@ -219,19 +248,15 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
         const int b = p / C, c = p - b * C;
         const int buf = (p - p0) & 1;
         if (p + 1 < p1) prefetch(p + 1, buf ^ 1);
-        if (b != cur_b) {  // CTA-uniform: the inverted index of a new cloud (the previous plane's readers passed the barrier below)
+        if (b != cur_b) {  // CTA-uniform: the index of a new cloud (the previous plane's readers passed the barrier at the loop's end)
             cur_b = b;
-            const int* __restrict__ start = start_all + (size_t)b * (N + 1);
             const int* __restrict__ list = list_all + (size_t)b * nk;
-            for (int n = tid; n <= N; n += kPlaneThreads) sStart[n] = __ldg(start + n);
+            const unsigned short* __restrict__ vfirst = vfirst_all + (size_t)b * (N + 1);
+            const unsigned short* __restrict__ vbeg = vbeg_all + (size_t)b * (vmax + 1);
+            V = __ldg(vfirst + N);
             for (int e = tid; e < nk; e += kPlaneThreads) sList[e] = (unsigned short)__ldg(list + e);
-            if (tid == 0) sNHub = 0;
-            __syncthreads();
-            myslot = -1;
-            if (tid < N && __ldg(start + tid + 1) - __ldg(start + tid) > kHubCap) {
-                myslot = atomicAdd(&sNHub, 1);
-                sHub[myslot] = (unsigned short)tid;
-            }
+            for (int n = tid; n <= N; n += kPlaneThreads) sVfirst[n] = __ldg(vfirst + n);
+            for (int v = tid; v <= V; v += kPlaneThreads) sVbeg[v] = __ldg(vbeg + v);
         }
         if (p + 1 < p1)
             asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -241,10 +266,22 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
 
         const float* __restrict__ plane = sPlane + (size_t)buf * nk;
         if (p + 1 < p1) load_centre(p + 1);  // consumed by fold_centre() below, after this plane's gathers
+        // (A) sub-bucket sums
+        for (int v = tid; v < V; v += kPlaneThreads) {
+            const int s0 = sVbeg[v], s1 = sVbeg[v + 1];
+            double part = 0.0;
+            for (int s_ = s0; s_ < s1; s_ += 4) {
+                float val[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) val[t] = s_ + t < s1 ? plane[sList[s_ + t]] : 0.f;
+                part += ((double)val[0] + (double)val[1]) + ((double)val[2] + (double)val[3]);
+            }
+            sPart[v] = part;
+        }
+        // the point's own k slots of the difference half (while the others finish their sub-buckets)
+        double acc = msum;
         if (tid < N) {
-            const int n = tid;
-            double acc = msum;
-            const float4* gd4 = reinterpret_cast<const float4*>(plane + n * k);
+            const float4* gd4 = reinterpret_cast<const float4*>(plane + tid * k);
 #pragma unroll
             for (int j = 0; j < kPlaneK4; ++j) {
                 if (j < k4) {
@@ -252,38 +289,22 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
                     acc -= ((double)d.x + (double)d.y) + ((double)d.z + (double)d.w);
                 }
             }
-            const int s0 = sStart[n], s1 = min(sStart[n + 1], s0 + kHubCap);
-            for (int s_ = s0; s_ < s1; s_ += 4) {
-                float v[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) v[t] = s_ + t < s1 ? plane[sList[s_ + t]] : 0.f;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) acc += (double)v[t];
-            }
-            if (myslot < 0)
-                gx[((size_t)b * C + c) * N + n] = (float)acc;
-            else
-                sHubAcc[myslot] = acc;
         }
         __syncthreads();
-        // the long tails of the hub points' buckets, a warp per hub
-        for (int h = w; h < sNHub; h += kPlaneThreads / 32) {
-            const int n = sHub[h];
-            const int s1 = sStart[n + 1];
-            double part = 0.0;
-            for (int s_ = sStart[n] + kHubCap + lane; s_ < s1; s_ += 32) part += (double)plane[sList[s_]];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-            if (lane == 0) gx[((size_t)b * C + c) * N + n] = (float)(sHubAcc[h] + part);
+        // (B) the point's sub-bucket sums, in index order
+        if (tid < N) {
+            const int v0 = sVfirst[tid], v1 = sVfirst[tid + 1];
+            for (int v = v0; v < v1; ++v) acc += sPart[v];
+            gx[((size_t)b * C + c) * N + tid] = (float)acc;
         }
         if (p + 1 < p1) msum = fold_centre();
-        __syncthreads();  // everyone is done with this buffer before the prefetch after next overwrites it
+        __syncthreads();  // everyone is done with this buffer and with sPart before the next plane overwrites them
     }
 }
 
 static size_t edge_plane_smem(int N, int k) {
-    const size_t nk = (size_t)N * k;
-    return 2 * nk * sizeof(float) + (size_t)(N + 1) * sizeof(int) + nk * sizeof(unsigned short);
+    const size_t nk = (size_t)N * k, vmax = (size_t)edge_plane_vmax(N, k);
+    return 2 * nk * sizeof(float) + vmax * sizeof(double) + (nk + vmax + 1 + (size_t)N + 1) * sizeof(unsigned short);
 }
 
 int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out, cudaStream_t stream) {
@@ -305,10 +326,18 @@ int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C
     return FPSG_OK;
 }
 
+static bool edge_plane_path(int N, int k) {
+    const long long nk = (long long)N * k;
+    return nk <= 65535 && (k & 3) == 0 && k <= 4 * kPlaneK4 && N <= kPlaneThreads && edge_plane_smem(N, k) <= 226 * 1024;
+}
+
 size_t edge_feature_backward_workspace(int B, int C, int N, int k) {
     (void)C;
     if (B <= 0 || N < 1 || k < 1) return 0;
-    return align_up((size_t)B * (N + 1) * sizeof(int), 256) + align_up((size_t)B * N * k * sizeof(int), 256);
+    size_t need = align_up((size_t)B * (N + 1) * sizeof(int), 256) + align_up((size_t)B * N * k * sizeof(int), 256);
+    if (edge_plane_path(N, k))  // the sub-bucket tables
+        need += align_up((size_t)B * (N + 1) * sizeof(unsigned short), 256) + align_up((size_t)B * (edge_plane_vmax(N, k) + 1) * sizeof(unsigned short), 256);
+    return need;
 }
 
 int edge_feature_backward_launch(const float* g, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws, size_t ws_bytes,
@@ -321,21 +350,32 @@ int edge_feature_backward_launch(const float* g, const int64_t* idx, int B, int 
     if ((size_t)(N + 1) * sizeof(int) > 200 * 1024) return fail(FPSG_EINVAL, "edge_feature_bwd: N=%d too large (shared-memory counters)", N);
     const size_t need = edge_feature_backward_workspace(B, C, N, k);
     if (!ws || ws_bytes < need) return fail(FPSG_EWORKSPACE, "edge_feature_bwd: workspace of %zu bytes required, %zu given", need, ws ? ws_bytes : (size_t)0);
-    int* start = static_cast<int*>(ws);
-    int* list = reinterpret_cast<int*>(static_cast<char*>(ws) + align_up((size_t)B * (N + 1) * sizeof(int), 256));
+    char* wp = static_cast<char*>(ws);
+    int* start = reinterpret_cast<int*>(wp);
+    wp += align_up((size_t)B * (N + 1) * sizeof(int), 256);
+    int* list = reinterpret_cast<int*>(wp);
+    wp += align_up((size_t)B * N * k * sizeof(int), 256);
+    const bool plane = edge_plane_path(N, k) && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && !tune_env("FPSG_EDGE_NOPLANE");
+    const int vmax = edge_plane_vmax(N, k);
+    unsigned short* vfirst = nullptr;
+    unsigned short* vbeg = nullptr;
+    if (plane) {
+        vfirst = reinterpret_cast<unsigned short*>(wp);
+        wp += align_up((size_t)B * (N + 1) * sizeof(unsigned short), 256);
+        vbeg = reinterpret_cast<unsigned short*>(wp);
+    }
     const size_t smem = (size_t)(N + 1) * sizeof(int);
     if (smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(edge_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_invert_kernel<<<B, 1024, smem, stream>>>(idx, N, k, start, list);
+    edge_invert_kernel<<<B, 1024, smem, stream>>>(idx, N, k, start, list, vfirst, vbeg, vmax + 1);
     FPSG_CUDA_OK(cudaGetLastError());
-    const long long nk = (long long)N * k;
-    const size_t psmem = edge_plane_smem(N, k);
-    if (nk <= 65535 && (k & 3) == 0 && k <= 4 * kPlaneK4 && N <= kPlaneThreads && psmem <= 212 * 1024 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && !tune_env("FPSG_EDGE_NOPLANE")) {
+    if (plane) {
+        const size_t psmem = edge_plane_smem(N, k);
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long planes = (long long)B * C;
         const unsigned grid = (unsigned)(planes < sms ? planes : sms);
         FPSG_CUDA_OK(cudaFuncSetAttribute(edge_feature_bwd_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        edge_feature_bwd_plane_kernel<<<grid, kPlaneThreads, psmem, stream>>>(g, start, list, B, C, N, k, gx);
+        edge_feature_bwd_plane_kernel<<<grid, kPlaneThreads, psmem, stream>>>(g, list, vfirst, vbeg, vmax, B, C, N, k, gx);
         FPSG_CUDA_OK(cudaGetLastError());
         return FPSG_OK;
     }
