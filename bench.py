@@ -232,6 +232,19 @@ def secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M)
                                              "path": "FP32 threshold-selection kernel (knn.cu)" if C_ == 3 else
                                                      "tcgen05 FP16 pre-filter + exact FP32 re-scoring of the marked candidates (knn_tc.cu); tflops = the "
                                                      "algorithmic (2C+2) N^2 FLOP of the reference's matmul formulation over the time, not an FP32 rate"}
+        if C_ in (3, 64) and NK_ == 1024:
+            # the EdgeConv graph feature that consumes this kNN graph (src/dgcnn/model.py:31-41): forward writes
+            # (B, 2C, N, k) once, backward reads it once -- both HBM-bound, reported against the measured copy bandwidth of MEASURED_PEAKS.json
+            ko = torch.empty(32, 2 * C_, NK_, 20, device=dev)
+            gxk = torch.empty(32, C_, NK_, device=dev)
+            nbe = L.fpsg_edge_feature_bwd_workspace_bytes(32, C_, NK_, 20)
+            wse = torch.empty(max(nbe, 1), dtype=torch.uint8, device=dev)
+            us_f = _timed_us(torch, stream, dev, lambda: _lib.check(L.fpsg_edge_feature_fwd(xk.data_ptr(), ik.data_ptr(), 32, C_, NK_, 20, ko.data_ptr(), sp)), 10)
+            us_b = _timed_us(torch, stream, dev, lambda: _lib.check(L.fpsg_edge_feature_bwd(ko.data_ptr(), ik.data_ptr(), 32, C_, NK_, 20, gxk.data_ptr(), wse.data_ptr(), nbe, sp)), 10)
+            nbytes = ko.numel() * 4
+            sec[f"edge_feature_k20_B32_N{NK_}_C{C_}"] = {"fwd_us": us_f, "fwd_gb_per_s_written": nbytes / us_f / 1e3, "bwd_us": us_b, "bwd_gb_per_s_read": nbytes / us_b / 1e3,
+                                                         "bytes": nbytes}
+            del ko, gxk, wse
         del xk, ik, wsk
 
     # ---- c2: one training step of 32 episodes = 32 x (5 query + 32 support) = 1184 pairs, N=M=2048
