@@ -63,6 +63,20 @@ def test_knn_every_dispatch_path_multi_tile(B, C, N, k):
     assert (got == ref).all(), f"{(got != ref).sum()} of {ref.size} positions differ"
 
 
+@pytest.mark.parametrize("B,N,k", [(1, 8192, 20), (1, 4100, 32), (2, 2048, 20), (2, 1024, 32), (2, 1024, 1), (1, 897, 20), (1, 896, 20), (2, 512, 20),
+                                   (2, 257, 7), (3, 64, 20), (2, 40, 32), (2, 33, 3)])
+def test_knn_xyz_selection_kernel_shape_space(B, N, k):
+    """knn_select_kernel (C = 3, k <= 32, N <= 8192) over its plan space: every fine-group size (8 .. 64 candidates), clouds with fewer
+    fine groups than the 64 coarse ones (empty coarse groups), the two-octet specialisation (896 < N <= 1024) and its neighbours,
+    k = 1 and k = 32 (the network's full width), clouds smaller than k groups (everything takes the streaming path)."""
+    import fpsg_b200
+    O = _oracle()
+    x = make_cloud_cn(B, 3, N, seed=11 * B + N + k)
+    got = fpsg_b200.knn(x.cuda(), k).cpu().numpy()
+    ref = O.knn_f32(x.numpy(), k)
+    assert (got == ref).all(), f"{(got != ref).sum()} of {ref.size} positions differ"
+
+
 def test_knn_duplicates_and_ties():
     import fpsg_b200
     O = _oracle()
