@@ -578,15 +578,19 @@ knn_gemm_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
 //           no ballots, no divergence. Only the maximum score of each of <= 128 contiguous "fine" candidate
 //           groups is kept (one float per group, in shared memory). Four warps share a group of 32 queries and
 //           scan a quarter of the candidates each, so that small batches still fill the chip.
-//   thresh  the fine maxima are folded into 32 coarse group maxima; their k-th largest value T (a 32-input
-//           bitonic network in the thread's registers) is a lower bound of the k-th largest score, because k
-//           different candidates reach it. About 31 candidates reach T for k = 20, N = 1024.
-//   final   a warp per query: it lists the fine groups whose maximum reaches T (ballot), re-scores only their
-//           candidates (about a fifth of the cloud), compacts the ones with pd >= T into <= 64 keys of
-//           (order-preserving pd bits, ~index), sorts them with a bitonic network and writes the first k indices.
-//           Two queries are processed together so that their shuffle chains overlap.
-// A query with more than 64 candidates >= T (heavily duplicated points: everything ties with T) is redone by
-// its warp with a streaming sort-and-merge over all N candidates, so the result is exact for any input.
+//   thresh  64 coarse group maxima (consecutive fine groups, exact values) per query; their k-th largest value T is a
+//           lower bound of the k-th largest score, because k different candidates reach it: every thread sorts its 16 with
+//           a bitonic network in registers, the query's first thread merges the four runs. About 24 candidates reach T
+//           for k = 20, N = 1024, and more than 32 do for one query in a thousand.
+//   lists   every thread lists the fine groups of its quarter whose maximum reaches T (about 22 of 128 per query).
+//   rescore the four lists of a query are dealt round-robin to its four threads; each re-scores its groups' candidates and
+//           appends the indices of those with pd >= T to its own shared-memory column.
+//   final   warp w takes the CTA's queries 8w .. 8w+7, four lanes per query: 8 keys of (order-preserving pd bits, ~index)
+//           per lane, a 32-key bitonic network spread over the four lanes' registers (shuffles only), the first k indices
+//           staged per warp and written as contiguous stores.
+// A query with more than 32 candidates >= T, a column overflow or fewer than k candidates (NaN scores) is sorted by its whole
+// warp: two bitonic rounds up to 64 candidates, else (heavily duplicated points: everything ties with T) a streaming
+// sort-and-merge over all N candidates, so the result is exact for any input.
 // pd is computed by the same instruction sequence everywhere (see the file header), so the stages agree bit for
 // bit. Padded candidates carry NaN in .w: their pd is NaN, max.f32 ignores it and `>=` rejects it.
 // ---------------------------------------------------------------------------------------------------------
@@ -778,7 +782,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
 
     // ---- pass 1: maxima of this warp's quarter of the fine groups, one query per thread ----
     // The fine maxima are kept rounded UP to 16 bits (they only decide which groups are re-scored: a superset is fine);
-    // the threshold needs exact values and gets the exact maxima of the 32 coarse groups (consecutive fine groups).
+    // the threshold needs exact values and gets the exact maxima of the 64 coarse groups (consecutive fine groups).
     {
         unsigned short* fm = sFm + ql * kSelFmStride;
         auto up16 = [](float v) {  // smallest 16-bit-truncated float >= v (truncation moves negative values up already)
