@@ -671,8 +671,8 @@ def main():
     e2e_s = sorted(e2e_reps)[1]
     pipe.close()
 
-    # ---- the floor under e2e: the same host->device copies alone (all ranks at once, nothing else running). On an 8-GPU box two
-    # GPUs share a PCIe switch uplink, so the copies of a step can take longer than its kernels; the line reports both ----
+    # ---- the floor under e2e: the same host->device copies alone (all ranks at once, nothing else running). On an 8-GPU box the
+    # host side delivers ~200 GB/s in total (25 GB/s per GPU), so the copies of a step can take longer than its kernels; the line reports both ----
     h2d_dst = [torch.empty_like(host[0][0], device=dev), torch.empty_like(host[0][1], device=dev)]
     copy_stream = torch.cuda.Stream(device=dev)
     h2d_iters = 300
