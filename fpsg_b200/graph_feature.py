@@ -12,6 +12,9 @@ from .knn import knn
 
 from .chamfer import _stream_ptr as _stream
 
+# one call of the library takes at most 65535 clouds (a grid dimension); the reference takes any batch size: larger batches go in chunks
+_MAX_CLOUDS_PER_CALL = 65535
+
 
 class _GraphFeature(torch.autograd.Function):
     @staticmethod
@@ -60,4 +63,7 @@ def get_graph_feature(x: torch.Tensor, k: int = 20, idx: torch.Tensor | None = N
         # one host synchronisation, on this path only -- DGCNNfeat.forward never passes idx
         if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= N):
             raise IndexError(f"idx values must lie in [0, {N}), got [{int(idx.min())}, {int(idx.max())}]")
+    if B > _MAX_CLOUDS_PER_CALL:
+        m = _MAX_CLOUDS_PER_CALL
+        return torch.cat([_GraphFeature.apply(x[s:s + m], idx[s:s + m]) for s in range(0, B, m)], dim=0)
     return _GraphFeature.apply(x, idx)

@@ -49,6 +49,27 @@ def test_forward_bit_exact_and_backward_vs_autograd(B, C, N, k):
 
 
 @pytest.mark.gpu
+def test_batches_beyond_one_call_are_chunked(monkeypatch):
+    """The library takes at most 65535 clouds per call; the wrapper chunks and stays differentiable (checked with a small chunk size)."""
+    import sys
+    import fpsg_b200
+    G = sys.modules["fpsg_b200.graph_feature"]
+    x = make_cloud_cn(7, 6, 50, seed=13)
+    w = torch.randn(7, 12, 50, 5, generator=torch.Generator().manual_seed(2)).cuda()
+
+    def run():
+        a = x.cuda().requires_grad_(True)
+        out = fpsg_b200.get_graph_feature(a, k=5)
+        (out * w).sum().backward()
+        return out.detach().clone(), a.grad.clone()
+
+    whole = run()
+    monkeypatch.setattr(G, "_MAX_CLOUDS_PER_CALL", 3)
+    parts = run()
+    assert torch.equal(whole[0], parts[0]) and torch.allclose(whole[1], parts[1], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.gpu
 def test_default_idx_path_and_dgcnn_patch():
     import sys
     import types
