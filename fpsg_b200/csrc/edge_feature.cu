@@ -194,6 +194,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 static int edge_plane_vmax(int N, int k) { return (int)(((long long)N * k) / kPlaneSub) + N; }  // sub-buckets of a cloud, at most
+constexpr int kPlaneSubPerThread = 3;  // sub-buckets a thread takes (v = tid, tid + 1024, tid + 2048): vmax <= 3072
 
 __global__ void __launch_bounds__(kPlaneThreads, 1)
 edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict__ list_all, const unsigned short* __restrict__ vfirst_all,
@@ -203,8 +204,6 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
     float* sPlane = reinterpret_cast<float*>(smem_raw);                            // [2][nk] difference-half planes
     double* sPart = reinterpret_cast<double*>(sPlane + 2 * (size_t)nk);             // [vmax] sub-bucket sums of the current plane
     unsigned short* sList = reinterpret_cast<unsigned short*>(sPart + vmax);       // [nk] slots, grouped by target point
-    unsigned short* sVbeg = sList + nk;                                            // [vmax + 1]
-    unsigned short* sVfirst = sVbeg + vmax + 1;                                    // [N + 1]
     const int tid = threadIdx.x;
     const long long planes = (long long)B * C;
     const int p0 = (int)(planes * blockIdx.x / gridDim.x), p1 = (int)(planes * (blockIdx.x + 1) / gridDim.x);
@@ -238,7 +237,12 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
     };
     double msum = 0.0;
 
-    int cur_b = -1, V = 0;
+    // per cloud, in registers: this thread's sub-buckets (first list position | length << 16; 0 = none) and its point's range of sums
+    unsigned mysub[kPlaneSubPerThread];
+#pragma unroll
+    for (int r = 0; r < kPlaneSubPerThread; ++r) mysub[r] = 0u;
+    int v0 = 0, v1 = 0;
+    int cur_b = -1;
     if (p0 < p1) {
         prefetch(p0, 0);
         load_centre(p0);
@@ -253,10 +257,19 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
             const int* __restrict__ list = list_all + (size_t)b * nk;
             const unsigned short* __restrict__ vfirst = vfirst_all + (size_t)b * (N + 1);
             const unsigned short* __restrict__ vbeg = vbeg_all + (size_t)b * (vmax + 1);
-            V = __ldg(vfirst + N);
+            const int V = __ldg(vfirst + N);
             for (int e = tid; e < nk; e += kPlaneThreads) sList[e] = (unsigned short)__ldg(list + e);
-            for (int n = tid; n <= N; n += kPlaneThreads) sVfirst[n] = __ldg(vfirst + n);
-            for (int v = tid; v <= V; v += kPlaneThreads) sVbeg[v] = __ldg(vbeg + v);
+#pragma unroll
+            for (int r = 0; r < kPlaneSubPerThread; ++r) {
+                const int v = tid + r * kPlaneThreads;
+                mysub[r] = 0u;
+                if (v < V) {
+                    const unsigned s0 = __ldg(vbeg + v), s1 = __ldg(vbeg + v + 1);
+                    mysub[r] = s0 | ((s1 - s0) << 16);
+                }
+            }
+            v0 = __ldg(vfirst + min(tid, N - 1));
+            v1 = tid < N ? (int)__ldg(vfirst + tid + 1) : v0;
         }
         if (p + 1 < p1)
             asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -266,17 +279,25 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
 
         const float* __restrict__ plane = sPlane + (size_t)buf * nk;
         if (p + 1 < p1) load_centre(p + 1);  // consumed by fold_centre() below, after this plane's gathers
-        // (A) sub-bucket sums
-        for (int v = tid; v < V; v += kPlaneThreads) {
-            const int s0 = sVbeg[v], s1 = sVbeg[v + 1];
-            double part = 0.0;
-            for (int s_ = s0; s_ < s1; s_ += 4) {
-                float val[4];
+        // (A) sub-bucket sums. Fully unrolled and predicated: the (up to) 16 list entries are loaded back to back, then the 16
+        // gathers, then one fixed summation tree -- as a loop of dependent round trips this phase ran at 30 % issue utilisation.
 #pragma unroll
-                for (int t = 0; t < 4; ++t) val[t] = s_ + t < s1 ? plane[sList[s_ + t]] : 0.f;
-                part += ((double)val[0] + (double)val[1]) + ((double)val[2] + (double)val[3]);
+        for (int r = 0; r < kPlaneSubPerThread; ++r) {
+            const int len = (int)(mysub[r] >> 16);
+            if (len != 0) {
+                const unsigned short* lp = sList + (mysub[r] & 0xffffu);
+                unsigned short e[kPlaneSub];
+#pragma unroll
+                for (int t = 0; t < kPlaneSub; ++t) e[t] = t < len ? lp[t] : (unsigned short)0;
+                float val[kPlaneSub];
+#pragma unroll
+                for (int t = 0; t < kPlaneSub; ++t) val[t] = t < len ? plane[e[t]] : 0.f;
+                double d4[kPlaneSub / 4];
+#pragma unroll
+                for (int t = 0; t < kPlaneSub / 4; ++t)
+                    d4[t] = ((double)val[4 * t] + (double)val[4 * t + 1]) + ((double)val[4 * t + 2] + (double)val[4 * t + 3]);
+                sPart[tid + r * kPlaneThreads] = (d4[0] + d4[1]) + (d4[2] + d4[3]);
             }
-            sPart[v] = part;
         }
         // the point's own k slots of the difference half (while the others finish their sub-buckets)
         double acc = msum;
@@ -293,7 +314,6 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
         __syncthreads();
         // (B) the point's sub-bucket sums, in index order
         if (tid < N) {
-            const int v0 = sVfirst[tid], v1 = sVfirst[tid + 1];
             for (int v = v0; v < v1; ++v) acc += sPart[v];
             gx[((size_t)b * C + c) * N + tid] = (float)acc;
         }
@@ -304,7 +324,7 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
 
 static size_t edge_plane_smem(int N, int k) {
     const size_t nk = (size_t)N * k, vmax = (size_t)edge_plane_vmax(N, k);
-    return 2 * nk * sizeof(float) + vmax * sizeof(double) + (nk + vmax + 1 + (size_t)N + 1) * sizeof(unsigned short);
+    return 2 * nk * sizeof(float) + vmax * sizeof(double) + nk * sizeof(unsigned short);
 }
 
 int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out, cudaStream_t stream) {
@@ -328,7 +348,8 @@ int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C
 
 static bool edge_plane_path(int N, int k) {
     const long long nk = (long long)N * k;
-    return nk <= 65535 && (k & 3) == 0 && k <= 4 * kPlaneK4 && N <= kPlaneThreads && edge_plane_smem(N, k) <= 226 * 1024;
+    return nk <= 65535 && (k & 3) == 0 && k <= 4 * kPlaneK4 && N <= kPlaneThreads && edge_plane_vmax(N, k) <= kPlaneSubPerThread * kPlaneThreads &&
+           edge_plane_smem(N, k) <= 226 * 1024;
 }
 
 size_t edge_feature_backward_workspace(int B, int C, int N, int k) {
