@@ -66,20 +66,23 @@ edge_feature_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__
 // start (N+1 ints) and list (N*k ints) live in the workspace. One CTA per cloud; counts in shared memory.
 // For the plane-staged backward the buckets are also cut into SUB-BUCKETS of at most kPlaneSub entries (kNN graphs of
 // high-dimensional features have hubs: a fifth of the points of a 64-channel cloud have more than 32 in-edges, some several
-// hundred): vfirst[n] = number of sub-buckets of the points before n (N+1 entries), vbeg[v] = first list position of
-// sub-bucket v (sub-buckets are consecutive pieces of the list; vbeg[V] = N*k). Both 16-bit (that path needs N*k <= 65535).
+// hundred): vfirst[n] = number of sub-buckets of the points before n (N+1 entries, 16-bit), sub[v] = first list position of
+// sub-bucket v | its length << 16. On that path every bucket starts on a multiple of 4 list entries -- 8 bytes of the 16-bit copy the
+// kernel keeps in shared memory, so four entries arrive per load -- which needs N*k + 3N <= 65535 (16-bit positions; the padding
+// entries are zeroed by the caller). list_stride = list entries per cloud.
 constexpr int kPlaneSub = 16;
 
 __global__ void __launch_bounds__(1024)
 edge_invert_kernel(const int64_t* __restrict__ idx, int N, int k, int* __restrict__ start_all, int* __restrict__ list_all,
-                   unsigned short* __restrict__ vfirst_all, unsigned short* __restrict__ vbeg_all, int vstride) {
+                   long long list_stride, unsigned short* __restrict__ vfirst_all, unsigned* __restrict__ sub_all, int vstride) {
     extern __shared__ int sCnt[];  // N + 1 counters, then reused as cursors
     __shared__ int sWarp[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const long long nk = (long long)N * k;
     const int64_t* __restrict__ ib = idx + (size_t)b * nk;
     int* __restrict__ start = start_all + (size_t)b * (N + 1);
-    int* __restrict__ list = list_all + (size_t)b * nk;
+    int* __restrict__ list = list_all + (size_t)b * list_stride;
+    const bool padded = vfirst_all != nullptr;
 
     for (int n = tid; n <= N; n += 1024) sCnt[n] = 0;
     __syncthreads();
@@ -118,23 +121,19 @@ edge_invert_kernel(const int64_t* __restrict__ idx, int N, int k, int* __restric
         }
         return carry;
     };
-    if (vfirst_all != nullptr) {  // sub-bucket tables (before the counters turn into cursors)
+    if (padded) {  // sub-bucket counts (before the counters turn into cursors)
         unsigned short* __restrict__ vfirst = vfirst_all + (size_t)b * (N + 1);
-        unsigned short* __restrict__ vbeg = vbeg_all + (size_t)b * vstride;
-        const int V = scan([&](int n) { return (sCnt[n] + kPlaneSub - 1) / kPlaneSub; },
-                           [&](int n, int excl, int) { vfirst[n] = (unsigned short)excl; });
-        if (tid == 0) {
-            vfirst[N] = (unsigned short)V;
-            vbeg[V] = (unsigned short)nk;
-        }
-        __syncthreads();  // vfirst is read back below by other threads' points? no: each thread reads its own n -- but keep the scan's sWarp settled
+        const int V = scan([&](int n) { return (sCnt[n] + kPlaneSub - 1) / kPlaneSub; }, [&](int n, int excl, int) { vfirst[n] = (unsigned short)excl; });
+        if (tid == 0) vfirst[N] = (unsigned short)V;
     }
-    const int total = scan([&](int n) { return sCnt[n]; },
-                           [&](int n, int excl, int c) {
+    const int total = scan([&](int n) { return padded ? (sCnt[n] + 3) & ~3 : sCnt[n]; },
+                           [&](int n, int excl, int) {
                                start[n] = excl;
-                               if (vfirst_all != nullptr) {
-                                   unsigned short* __restrict__ vbeg = vbeg_all + (size_t)b * vstride + vfirst_all[(size_t)b * (N + 1) + n];
-                                   for (int j = 0; j * kPlaneSub < c; ++j) vbeg[j] = (unsigned short)(excl + j * kPlaneSub);
+                               if (padded) {
+                                   const int c = sCnt[n];
+                                   unsigned* __restrict__ sub = sub_all + (size_t)b * vstride + vfirst_all[(size_t)b * (N + 1) + n];
+                                   for (int j = 0; j * kPlaneSub < c; ++j)
+                                       sub[j] = (unsigned)(excl + j * kPlaneSub) | ((unsigned)min(kPlaneSub, c - j * kPlaneSub) << 16);
                                }
                                sCnt[n] = excl;  // cursor
                            });
@@ -194,16 +193,17 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 static int edge_plane_vmax(int N, int k) { return (int)(((long long)N * k) / kPlaneSub) + N; }  // sub-buckets of a cloud, at most
+static int edge_plane_list(int N, int k) { return N * k + 3 * N; }                                // list entries of a cloud with 4-entry aligned buckets, at most
 constexpr int kPlaneSubPerThread = 3;  // sub-buckets a thread takes (v = tid, tid + 1024, tid + 2048): vmax <= 3072
 
 __global__ void __launch_bounds__(kPlaneThreads, 1)
 edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict__ list_all, const unsigned short* __restrict__ vfirst_all,
-                              const unsigned short* __restrict__ vbeg_all, int vmax, int B, int C, int N, int k, float* __restrict__ gx) {
+                              const unsigned* __restrict__ sub_all, int vmax, int nlist, int B, int C, int N, int k, float* __restrict__ gx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nk = N * k;
     float* sPlane = reinterpret_cast<float*>(smem_raw);                            // [2][nk] difference-half planes
     double* sPart = reinterpret_cast<double*>(sPlane + 2 * (size_t)nk);             // [vmax] sub-bucket sums of the current plane
-    unsigned short* sList = reinterpret_cast<unsigned short*>(sPart + vmax);       // [nk] slots, grouped by target point
+    unsigned short* sList = reinterpret_cast<unsigned short*>(sPart + vmax);       // [nlist] slots grouped by target point, buckets 8-byte aligned
     const int tid = threadIdx.x;
     const long long planes = (long long)B * C;
     const int p0 = (int)(planes * blockIdx.x / gridDim.x), p1 = (int)(planes * (blockIdx.x + 1) / gridDim.x);
@@ -254,19 +254,15 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
         if (p + 1 < p1) prefetch(p + 1, buf ^ 1);
         if (b != cur_b) {  // CTA-uniform: the index of a new cloud (the previous plane's readers passed the barrier at the loop's end)
             cur_b = b;
-            const int* __restrict__ list = list_all + (size_t)b * nk;
+            const int* __restrict__ list = list_all + (size_t)b * nlist;
             const unsigned short* __restrict__ vfirst = vfirst_all + (size_t)b * (N + 1);
-            const unsigned short* __restrict__ vbeg = vbeg_all + (size_t)b * (vmax + 1);
+            const unsigned* __restrict__ sub = sub_all + (size_t)b * vmax;
             const int V = __ldg(vfirst + N);
-            for (int e = tid; e < nk; e += kPlaneThreads) sList[e] = (unsigned short)__ldg(list + e);
+            for (int e = tid; e < nlist; e += kPlaneThreads) sList[e] = (unsigned short)__ldg(list + e);
 #pragma unroll
             for (int r = 0; r < kPlaneSubPerThread; ++r) {
                 const int v = tid + r * kPlaneThreads;
-                mysub[r] = 0u;
-                if (v < V) {
-                    const unsigned s0 = __ldg(vbeg + v), s1 = __ldg(vbeg + v + 1);
-                    mysub[r] = s0 | ((s1 - s0) << 16);
-                }
+                mysub[r] = v < V ? __ldg(sub + v) : 0u;
             }
             v0 = __ldg(vfirst + min(tid, N - 1));
             v1 = tid < N ? (int)__ldg(vfirst + tid + 1) : v0;
@@ -285,10 +281,13 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
         for (int r = 0; r < kPlaneSubPerThread; ++r) {
             const int len = (int)(mysub[r] >> 16);
             if (len != 0) {
-                const unsigned short* lp = sList + (mysub[r] & 0xffffu);
-                unsigned short e[kPlaneSub];
+                const uint2* lp = reinterpret_cast<const uint2*>(sList + (mysub[r] & 0xffffu));  // 8-byte aligned: four entries per load
+                unsigned e[kPlaneSub];
 #pragma unroll
-                for (int t = 0; t < kPlaneSub; ++t) e[t] = t < len ? lp[t] : (unsigned short)0;
+                for (int q = 0; q < kPlaneSub / 4; ++q) {
+                    const uint2 w4 = 4 * q < len ? lp[q] : make_uint2(0u, 0u);
+                    e[4 * q] = w4.x & 0xffffu, e[4 * q + 1] = w4.x >> 16, e[4 * q + 2] = w4.y & 0xffffu, e[4 * q + 3] = w4.y >> 16;
+                }
                 float val[kPlaneSub];
 #pragma unroll
                 for (int t = 0; t < kPlaneSub; ++t) val[t] = t < len ? plane[e[t]] : 0.f;
@@ -324,7 +323,7 @@ edge_feature_bwd_plane_kernel(const float* __restrict__ g, const int* __restrict
 
 static size_t edge_plane_smem(int N, int k) {
     const size_t nk = (size_t)N * k, vmax = (size_t)edge_plane_vmax(N, k);
-    return 2 * nk * sizeof(float) + vmax * sizeof(double) + nk * sizeof(unsigned short);
+    return 2 * nk * sizeof(float) + vmax * sizeof(double) + (size_t)edge_plane_list(N, k) * sizeof(unsigned short);
 }
 
 int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out, cudaStream_t stream) {
@@ -348,16 +347,17 @@ int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C
 
 static bool edge_plane_path(int N, int k) {
     const long long nk = (long long)N * k;
-    return nk <= 65535 && (k & 3) == 0 && k <= 4 * kPlaneK4 && N <= kPlaneThreads && edge_plane_vmax(N, k) <= kPlaneSubPerThread * kPlaneThreads &&
+    return nk + 3LL * N <= 65535 && (k & 3) == 0 && k <= 4 * kPlaneK4 && N <= kPlaneThreads && edge_plane_vmax(N, k) <= kPlaneSubPerThread * kPlaneThreads &&
            edge_plane_smem(N, k) <= 226 * 1024;
 }
 
 size_t edge_feature_backward_workspace(int B, int C, int N, int k) {
     (void)C;
     if (B <= 0 || N < 1 || k < 1) return 0;
-    size_t need = align_up((size_t)B * (N + 1) * sizeof(int), 256) + align_up((size_t)B * N * k * sizeof(int), 256);
+    // (the list is sized for the padded layout of the plane path whether or not the call takes it: that also depends on the alignment of g)
+    size_t need = align_up((size_t)B * (N + 1) * sizeof(int), 256) + align_up((size_t)B * ((size_t)N * k + 3 * (size_t)N) * sizeof(int), 256);
     if (edge_plane_path(N, k))  // the sub-bucket tables
-        need += align_up((size_t)B * (N + 1) * sizeof(unsigned short), 256) + align_up((size_t)B * (edge_plane_vmax(N, k) + 1) * sizeof(unsigned short), 256);
+        need += align_up((size_t)B * (N + 1) * sizeof(unsigned short), 256) + align_up((size_t)B * edge_plane_vmax(N, k) * sizeof(unsigned), 256);
     return need;
 }
 
@@ -375,19 +375,20 @@ int edge_feature_backward_launch(const float* g, const int64_t* idx, int B, int 
     int* start = reinterpret_cast<int*>(wp);
     wp += align_up((size_t)B * (N + 1) * sizeof(int), 256);
     int* list = reinterpret_cast<int*>(wp);
-    wp += align_up((size_t)B * N * k * sizeof(int), 256);
+    wp += align_up((size_t)B * ((size_t)N * k + 3 * (size_t)N) * sizeof(int), 256);
     const bool plane = edge_plane_path(N, k) && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && !tune_env("FPSG_EDGE_NOPLANE");
-    const int vmax = edge_plane_vmax(N, k);
+    const int vmax = edge_plane_vmax(N, k), nlist = edge_plane_list(N, k);
     unsigned short* vfirst = nullptr;
-    unsigned short* vbeg = nullptr;
+    unsigned* vbeg = nullptr;
     if (plane) {
         vfirst = reinterpret_cast<unsigned short*>(wp);
         wp += align_up((size_t)B * (N + 1) * sizeof(unsigned short), 256);
-        vbeg = reinterpret_cast<unsigned short*>(wp);
+        vbeg = reinterpret_cast<unsigned*>(wp);
+        FPSG_CUDA_OK(cudaMemsetAsync(list, 0, (size_t)B * nlist * sizeof(int), stream));  // the padding entries of the list: slot 0
     }
     const size_t smem = (size_t)(N + 1) * sizeof(int);
     if (smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(edge_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    edge_invert_kernel<<<B, 1024, smem, stream>>>(idx, N, k, start, list, vfirst, vbeg, vmax + 1);
+    edge_invert_kernel<<<B, 1024, smem, stream>>>(idx, N, k, start, list, plane ? (long long)nlist : (long long)N * k, vfirst, vbeg, vmax);
     FPSG_CUDA_OK(cudaGetLastError());
     if (plane) {
         const size_t psmem = edge_plane_smem(N, k);
@@ -396,7 +397,7 @@ int edge_feature_backward_launch(const float* g, const int64_t* idx, int B, int 
         const long long planes = (long long)B * C;
         const unsigned grid = (unsigned)(planes < sms ? planes : sms);
         FPSG_CUDA_OK(cudaFuncSetAttribute(edge_feature_bwd_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        edge_feature_bwd_plane_kernel<<<grid, kPlaneThreads, psmem, stream>>>(g, list, vfirst, vbeg, vmax, B, C, N, k, gx);
+        edge_feature_bwd_plane_kernel<<<grid, kPlaneThreads, psmem, stream>>>(g, list, vfirst, vbeg, vmax, nlist, B, C, N, k, gx);
         FPSG_CUDA_OK(cudaGetLastError());
         return FPSG_OK;
     }
