@@ -595,15 +595,22 @@ knn_gemm_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
 // bit. Padded candidates carry NaN in .w: their pd is NaN, max.f32 ignores it and `>=` rejects it.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kSelS = 4;                        // warps that share 32 queries in pass 1
-constexpr int kSelThreads = 256;
-constexpr int kSelQ = kSelThreads / kSelS;      // queries per CTA
+// A CTA holds QW groups of 32 queries (QW = 1 or 2: 128 or 256 threads). c3 (N = 1024) takes QW = 1: 1024 CTAs of 31 KB, seven per
+// SM, fill 148 SMs almost evenly (6.9 per SM), where 512 CTAs of 50 KB leave 68 SMs with four and 80 with three.
+template <int QW>
+struct SelCfg {
+    static constexpr int Threads = 128 * QW;
+    static constexpr int Q = 32 * QW;                                   // queries per CTA
+    static constexpr int ColCap = QW == 1 ? 40 : 48;                    // candidate slots per thread column (one of the four shares of a query)
+    static constexpr size_t RegionA = (size_t)ColCap * Threads * 2;     // fine maxima + coarse maxima, later the candidate columns
+    static constexpr size_t RegionB = (size_t)Q * 66 * 2;               // (tail of the coarse maxima,) group lists, sorted indices
+    static constexpr size_t FmBytes = (size_t)Q * 130 * 2;              // fine maxima, at the head of region A
+};
 constexpr int kSelGroups = 64;                  // coarse groups (>= k): their k-th largest maximum is the threshold
 constexpr int kSelGpp = kSelGroups / kSelS;     // coarse groups per part (sorted in that thread's registers)
 constexpr int kSelFine = 128;                   // most fine groups per cloud
 constexpr int kSelFmStride = kSelFine + 2;      // 16-bit elements per query row of the fine maxima (65 words: conflict-free)
 constexpr int kSelCap = 64;                     // candidates per query
-constexpr int kSelColCap = 48;                  // candidate slots per thread column (one of the four shares of a query)
-constexpr int kSelListStride = kSelCap + 2;     // u16 elements per query row of the candidate lists
 constexpr int kSelMaxN = 8192;                  // the cloud must fit shared memory as float4
 
 __device__ __forceinline__ float knn_pd3(const float4 q, const float xxi, const float4 c) {
@@ -718,28 +725,40 @@ struct KnnSelPlan {
     int fsh;     // log2(candidates per fine group), >= 3
     int nfine;   // fine groups (<= kSelFine), all holding at least one real candidate
     int npad;    // nfine << fsh
+    int qw;      // groups of 32 queries per CTA
     size_t smem;
 };
-constexpr size_t kSelRegionA = (size_t)kSelColCap * kSelThreads * sizeof(unsigned short);  // fine maxima, later the candidate columns
-constexpr size_t kSelRegionB = (size_t)kSelQ * kSelListStride * sizeof(unsigned short);    // coarse maxima, group lists, query lists
-constexpr size_t kSelFmBytes = (size_t)kSelQ * kSelFmStride * sizeof(unsigned short);         // fine maxima, at the head of region A
-static_assert(kSelFmBytes % 16 == 0 && kSelFmBytes + (size_t)kSelGroups * kSelQ * sizeof(float) <= kSelRegionA + kSelRegionB,
-              "the exact coarse maxima ([64][Q] floats) fit behind the fine maxima: the tail of region A and all of region B");
-static_assert(kSelRegionB >= (size_t)(kSelFine / kSelS) * kSelThreads, "region B holds the per-thread group lists");
-static_assert((size_t)(kSelThreads / 32) * 256 * sizeof(unsigned short) <= kSelRegionB, "the warps' sorted indices of the final phase fit region B");
+template <int QW>
+constexpr bool sel_cfg_ok() {
+    using Cf = SelCfg<QW>;
+    return Cf::FmBytes % 16 == 0 && Cf::FmBytes + (size_t)kSelGroups * Cf::Q * sizeof(unsigned short) <= Cf::RegionA + Cf::RegionB  // coarse maxima behind the fine ones
+           && Cf::RegionB >= (size_t)(kSelFine / kSelS) * Cf::Threads                                                              // the per-thread group lists
+           && (size_t)(Cf::Threads / 32) * 256 * sizeof(unsigned short) <= Cf::RegionB;                                            // the warps' sorted indices
+}
+static_assert(sel_cfg_ok<1>() && sel_cfg_ok<2>(), "shared-memory regions of knn_select_kernel");
+template <int QW>
+static size_t knn_select_smem(int ntile) {
+    using Cf = SelCfg<QW>;
+    return (size_t)ntile * sizeof(float4) + Cf::RegionA + Cf::RegionB + (size_t)Cf::Q * sizeof(float) + 2 * (size_t)Cf::Threads;
+}
 static KnnSelPlan knn_select_plan(int N) {
     KnnSelPlan p;
     p.fsh = 3;
     while (((long long)kSelFine << p.fsh) < N) ++p.fsh;
     p.nfine = (N + (1 << p.fsh) - 1) >> p.fsh;
     p.npad = p.nfine << p.fsh;
-    p.smem = (size_t)(p.npad + (1 << p.fsh)) * sizeof(float4) + kSelRegionA + kSelRegionB + (size_t)kSelQ * sizeof(float) +
-             2 * (size_t)kSelThreads * sizeof(signed char);  // ~50 KB at N = 1024: four CTAs per SM
+    const int ntile = p.npad + (1 << p.fsh);
+    // small CTAs when seven of them fit an SM (N <= 1024: 31 KB each), else the 256-thread shape (N = 2048: 66 KB, three per SM)
+    p.qw = (knn_select_smem<1>(ntile) + 1024) * 7 <= 228 * 1024 ? 1 : 2;
+    p.smem = p.qw == 1 ? knn_select_smem<1>(ntile) : knn_select_smem<2>(ntile);
     return p;
 }
 
-__global__ void __launch_bounds__(kSelThreads)
+template <int QW>
+__global__ void __launch_bounds__(SelCfg<QW>::Threads)
 knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh, int64_t* __restrict__ idx) {
+    constexpr int kSelThreads = SelCfg<QW>::Threads, kSelQ = SelCfg<QW>::Q, kSelColCap = SelCfg<QW>::ColCap;
+    constexpr size_t kSelRegionA = SelCfg<QW>::RegionA, kSelRegionB = SelCfg<QW>::RegionB, kSelFmBytes = SelCfg<QW>::FmBytes;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int npad = nfine << fsh;
     const int ntile = npad + (1 << fsh);  // one more fine group, all padding: where idle lanes point
@@ -748,7 +767,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     unsigned char* regB = regA + kSelRegionA;
     unsigned short* sFm = reinterpret_cast<unsigned short*>(regA);                    // [Q][130] fine group maxima, rounded UP to 16 bits ...
     unsigned short* sBuf = reinterpret_cast<unsigned short*>(regA);                   // ... then [48][T] candidate columns
-    float* sScr = reinterpret_cast<float*>(regA + kSelFmBytes);                       // [64][Q] exact coarse maxima (then sorted): tail of A + B ...
+    unsigned short* sScr = reinterpret_cast<unsigned short*>(regA + kSelFmBytes);     // [64][Q] coarse maxima rounded DOWN to 16 bits (then sorted): tail of A (+ B) ...
     unsigned char* sGl = regB;                                                        // ... then [32][T] fine groups to re-score ...
     float* sThr = reinterpret_cast<float*>(regB + kSelRegionB);                       // [Q]
     signed char* sCntP = reinterpret_cast<signed char*>(sThr + kSelQ);                // [T] candidates found by a thread, -1 = overflow
@@ -789,6 +808,12 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
             const unsigned u = __float_as_uint(v);
             return (unsigned short)(((u >> 31) ? u : u + 0xffffu) >> 16);
         };
+        // largest 16-bit-truncated float <= v: the threshold may be any lower bound of the k-th largest score (a lower one lets a few
+        // more candidates through: 2^-8 of |T| is a tenth of a candidate at c3), and 16-bit coarse maxima halve their shared memory
+        auto down16 = [](float v) {
+            const unsigned u = __float_as_uint(v);
+            return (unsigned short)(((u >> 31) ? min(u + 0xffffu, 0xff800000u) : u) >> 16);  // (negative: magnitude up, saturating at -INF)
+        };
         if (fsh == 3 && nfine == 2 * kSelGroups) {  // 896 < N <= 1024 (c3): every coarse group is exactly two octets, no loop control at all
 #pragma unroll 1
             for (int c = part * kSelGpp; c < (part + 1) * kSelGpp; ++c) {
@@ -802,7 +827,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
                     m2[h] = max3(max3(max3(p[0], p[1], p[2]), p[3], p[4]), max3(p[5], p[6], p[7]), p[0]);
                 }
                 *reinterpret_cast<unsigned*>(fm + 2 * c) = (unsigned)up16(__fsub_rn(m2[0], xxi)) | ((unsigned)up16(__fsub_rn(m2[1], xxi)) << 16);
-                sScr[c * kSelQ + ql] = __fsub_rn(fmaxf(m2[0], m2[1]), xxi);
+                sScr[c * kSelQ + ql] = down16(__fsub_rn(fmaxf(m2[0], m2[1]), xxi));
             }
         } else
 #pragma unroll 1
@@ -837,7 +862,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
                     cmax = fmaxf(cmax, m);
                 }
             }
-            sScr[c * kSelQ + ql] = __fsub_rn(cmax, xxi);
+            sScr[c * kSelQ + ql] = down16(__fsub_rn(cmax, xxi));
         }
     }
 
@@ -846,11 +871,11 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
     {
         float v[kSelGpp];
 #pragma unroll
-        for (int r = 0; r < kSelGpp; ++r) v[r] = sScr[(part * kSelGpp + r) * kSelQ + ql];
+        for (int r = 0; r < kSelGpp; ++r) v[r] = __uint_as_float((unsigned)sScr[(part * kSelGpp + r) * kSelQ + ql] << 16);
         regs_sort_desc<kSelGpp>(v);
         if (part != 0) {
 #pragma unroll
-            for (int r = 0; r < kSelGpp; ++r) sScr[(part * kSelGpp + r) * kSelQ + ql] = v[r];
+            for (int r = 0; r < kSelGpp; ++r) sScr[(part * kSelGpp + r) * kSelQ + ql] = (unsigned short)(__float_as_uint(v[r]) >> 16);
         }
         __syncthreads();
         if (part == 0) {
@@ -858,7 +883,7 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
             // run 0 (registers) and run 1: the half-cleaner leaves the 16 largest of the 32 in t[0..15], all >= t[16..31], both bitonic
 #pragma unroll
             for (int r = 0; r < kSelGpp; ++r) {
-                const float o = sScr[(kSelGpp + (kSelGpp - 1 - r)) * kSelQ + ql];
+                const float o = __uint_as_float((unsigned)sScr[(kSelGpp + (kSelGpp - 1 - r)) * kSelQ + ql] << 16);
                 t[r] = fmaxf(v[r], o);
                 t[kSelGpp + r] = fminf(v[r], o);
             }
@@ -875,13 +900,13 @@ knn_select_kernel(const float* __restrict__ x, int N, int k, int nfine, int fsh,
 #pragma unroll
             for (int run = 2; run < kSelS; ++run) {
 #pragma unroll
-                for (int r = 0; r < kSelGpp; ++r) t[31 - r] = fmaxf(t[31 - r], sScr[(run * kSelGpp + r) * kSelQ + ql]);
+                for (int r = 0; r < kSelGpp; ++r) t[31 - r] = fmaxf(t[31 - r], __uint_as_float((unsigned)sScr[(run * kSelGpp + r) * kSelQ + ql] << 16));
                 regs_merge_desc<32>(t);
             }
             // t[k-1] without dynamic register indexing: through shared memory (this thread's own slots)
 #pragma unroll
-            for (int c = 0; c < 32; ++c) sScr[c * kSelQ + ql] = t[c];
-            sThr[ql] = sScr[(k - 1) * kSelQ + ql];
+            for (int c = 0; c < 32; ++c) sScr[c * kSelQ + ql] = (unsigned short)(__float_as_uint(t[c]) >> 16);  // (all 16-bit values: lossless)
+            sThr[ql] = __uint_as_float((unsigned)sScr[(k - 1) * kSelQ + ql] << 16);
         }
     }
     __syncthreads();
@@ -1453,8 +1478,13 @@ int knn_forward_launch(const float* x, int B, int C, int N, int k, int64_t* idx,
     if (!ws || ws_bytes < p.ws_bytes) return fail(FPSG_EWORKSPACE, "knn: workspace of %zu bytes required, %zu given", p.ws_bytes, ws ? ws_bytes : (size_t)0);
     if (C == 3 && k <= 32 && N <= kSelMaxN && !tune_env("FPSG_KNN_BULK")) {  // threshold-selection kernel (needs no workspace)
         const KnnSelPlan sp = knn_select_plan(N);
-        if (sp.smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
-        knn_select_kernel<<<dim3((unsigned)cdiv(N, kSelQ), (unsigned)B), kSelThreads, sp.smem, stream>>>(x, N, k, sp.nfine, sp.fsh, idx);
+        if (sp.qw == 1) {
+            if (sp.smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
+            knn_select_kernel<1><<<dim3((unsigned)cdiv(N, SelCfg<1>::Q), (unsigned)B), SelCfg<1>::Threads, sp.smem, stream>>>(x, N, k, sp.nfine, sp.fsh, idx);
+        } else {
+            if (sp.smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
+            knn_select_kernel<2><<<dim3((unsigned)cdiv(N, SelCfg<2>::Q), (unsigned)B), SelCfg<2>::Threads, sp.smem, stream>>>(x, N, k, sp.nfine, sp.fsh, idx);
+        }
         FPSG_CUDA_OK(cudaGetLastError());
         return FPSG_OK;
     }
