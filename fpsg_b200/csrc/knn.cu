@@ -578,7 +578,7 @@ knn_gemm_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C
 //           no ballots, no divergence. Only the maximum score of each of <= 128 contiguous "fine" candidate
 //           groups is kept (one float per group, in shared memory). Four warps share a group of 32 queries and
 //           scan a quarter of the candidates each, so that small batches still fill the chip.
-//   thresh  64 coarse group maxima (consecutive fine groups, exact values) per query; their k-th largest value T is a
+//   thresh  64 coarse group maxima (consecutive fine groups, kept as 16-bit lower bounds) per query; their k-th largest value T is a
 //           lower bound of the k-th largest score, because k different candidates reach it: every thread sorts its 16 with
 //           a bitonic network in registers, the query's first thread merges the four runs. About 24 candidates reach T
 //           for k = 20, N = 1024, and more than 32 do for one query in a thousand.
