@@ -226,7 +226,7 @@ def secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M)
         ik = torch.empty(32, NK_, 20, dtype=torch.int64, device=dev)
         nbk = L.fpsg_knn_workspace_bytes(32, C_, NK_, 20)
         wsk = torch.empty(max(nbk, 1), dtype=torch.uint8, device=dev)
-        us = _timed_us(torch, stream, dev, lambda: _lib.check(L.fpsg_knn_fwd(xk.data_ptr(), 32, C_, NK_, 20, ik.data_ptr(), wsk.data_ptr(), nbk, sp)), 20)
+        us = _timed_us(torch, stream, dev, lambda: _lib.check(L.fpsg_knn_fwd(xk.data_ptr(), 32, C_, NK_, 20, ik.data_ptr(), wsk.data_ptr(), nbk, sp)), 50, warm=5)
         tf = (2 * C_ + 2) * 32 * NK_ * NK_ / us / 1e6
         sec[("c3_" if NK_ == 1024 else "") + f"knn_k20_B32_N{NK_}_C{C_}"] = {"us_per_call": us, "clouds_per_s": 32 / us * 1e6, "tflops": tf, "frac_of_fp32_peak": tf / fp32_peak_tflops,
                                              "path": "FP32 threshold-selection kernel (knn.cu)" if C_ == 3 else
