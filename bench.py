@@ -242,8 +242,10 @@ def secondary_configs(torch, L, _lib, dev, stream, fp32_peak_tflops, ptrs, N, M)
             us_f = _timed_us(torch, stream, dev, lambda: _lib.check(L.fpsg_edge_feature_fwd(xk.data_ptr(), ik.data_ptr(), 32, C_, NK_, 20, ko.data_ptr(), sp)), 10)
             us_b = _timed_us(torch, stream, dev, lambda: _lib.check(L.fpsg_edge_feature_bwd(ko.data_ptr(), ik.data_ptr(), 32, C_, NK_, 20, gxk.data_ptr(), wse.data_ptr(), nbe, sp)), 10)
             nbytes = ko.numel() * 4
+            hbm = _hbm_peak()
             sec[f"edge_feature_k20_B32_N{NK_}_C{C_}"] = {"fwd_us": us_f, "fwd_gb_per_s_written": nbytes / us_f / 1e3, "bwd_us": us_b, "bwd_gb_per_s_read": nbytes / us_b / 1e3,
-                                                         "bytes": nbytes}
+                                                         "bytes": nbytes, "hbm_copy_peak_gb_per_s": hbm, "fwd_frac_of_hbm_peak": nbytes / us_f / 1e3 / hbm,
+                                                         "bwd_frac_of_hbm_peak": nbytes / us_b / 1e3 / hbm}
             del ko, gxk, wse
         del xk, ik, wsk
 
