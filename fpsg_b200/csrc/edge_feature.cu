@@ -62,6 +62,51 @@ edge_feature_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__
     }
 }
 
+// The same forward with the channel's row of x staged in shared memory (two rows in flight, 16-byte cp.async): gathering a row
+// straight from global memory costs an L1 wavefront per 128-byte line a warp touches (about 20 per gather instruction for a random
+// kNN graph) -- 3.9 TB/s written, bound by the load/store unit, not by HBM; from shared memory a gather is 3-4 wavefronts.
+// Needs k % 4 == 0 (the four slots of a thread then belong to one centre point), N % 4 == 0 and 16-byte aligned x.
+__global__ void __launch_bounds__(kEdgeThreads)
+edge_feature_fwd_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, int C, int N, int k, float* __restrict__ out) {
+    extern __shared__ __align__(16) float sRows[];  // [2][N]
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const long long nk = (long long)N * k;
+    const long long e0 = ((long long)blockIdx.x * kEdgeThreads + tid) * 4;
+    const bool live = e0 < nk;
+    const float* __restrict__ xb = x + (size_t)b * C * N;
+    float* __restrict__ ob = out + (size_t)b * 2 * C * nk;
+    int nb[4] = {0, 0, 0, 0};
+    int ctr = 0;
+    if (live) {
+        const int64_t* __restrict__ ib = idx + (size_t)b * nk + e0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) nb[t] = (int)ib[t];
+        ctr = (int)(e0 / k);
+    }
+    auto prefetch = [&](int c) {
+        const float4* src = reinterpret_cast<const float4*>(xb + (size_t)c * N);
+        float4* dst = reinterpret_cast<float4*>(sRows + (size_t)(c & 1) * N);
+        for (int q = tid; q < (N >> 2); q += kEdgeThreads) {
+            const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst + q));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + q) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(0);
+    for (int c = 0; c < C; ++c) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // row c is complete for everyone, and everyone is done with row c - 1 (whose buffer the next prefetch overwrites)
+        if (c + 1 < C) prefetch(c + 1);
+        if (live) {
+            const float* __restrict__ row = sRows + (size_t)(c & 1) * N;
+            const float m = row[ctr];
+            const float4 d = make_float4(__fsub_rn(row[nb[0]], m), __fsub_rn(row[nb[1]], m), __fsub_rn(row[nb[2]], m), __fsub_rn(row[nb[3]], m));
+            __stcs(reinterpret_cast<float4*>(ob + (size_t)c * nk + e0), d);
+            __stcs(reinterpret_cast<float4*>(ob + (size_t)(C + c) * nk + e0), make_float4(m, m, m, m));
+        }
+    }
+}
+
 // inverted index of idx for one cloud: for every point n the list of slots e = n'*k + j with idx[e] == n.
 // start (N+1 ints) and list (N*k ints) live in the workspace. One CTA per cloud; counts in shared memory.
 // For the plane-staged backward the buckets are also cut into SUB-BUCKETS of at most kPlaneSub entries (kNN graphs of
@@ -334,7 +379,12 @@ int edge_feature_forward_launch(const float* x, const int64_t* idx, int B, int C
     const long long nk = (long long)N * k;
     if (nk > 0x7fffffffLL) return fail(FPSG_EINVAL, "edge_feature: N*k too large");
     const bool vec4 = (nk % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    if (vec4) {
+    const size_t rows_smem = 2 * (size_t)N * sizeof(float);
+    if (vec4 && (k & 3) == 0 && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && rows_smem <= 96 * 1024 && C >= 8 && !tune_env("FPSG_EDGE_NOROWS")) {
+        const dim3 grid((unsigned)((nk / 4 + kEdgeThreads - 1) / kEdgeThreads), (unsigned)B);
+        if (rows_smem > 48 * 1024) FPSG_CUDA_OK(cudaFuncSetAttribute(edge_feature_fwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+        edge_feature_fwd_rows_kernel<<<grid, kEdgeThreads, rows_smem, stream>>>(x, idx, C, N, k, out);
+    } else if (vec4) {
         const dim3 grid((unsigned)((nk / 4 + kEdgeThreads - 1) / kEdgeThreads), (unsigned)B);
         edge_feature_fwd_kernel<true><<<grid, kEdgeThreads, 0, stream>>>(x, idx, C, N, k, out);
     } else {
